@@ -1,0 +1,166 @@
+// common.cuh -- context, error plumbing and host<->device staging shared by every stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include "../../include/ofb200.h"
+
+void ofb_set_error(const char* fmt, ...);
+
+#define OFB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ofb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return OFB_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define OFB_REQUIRE(cond, ...)                                                                  \
+    do {                                                                                        \
+        if (!(cond)) { ofb_set_error(__VA_ARGS__); return OFB_E_INVALID; }                      \
+    } while (0)
+
+#define OFB_TRY(call)                                                                           \
+    do { int r__ = (call); if (r__ != OFB_OK) return r__; } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return OFB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            ofb_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return OFB_E_NOMEM;
+        }
+        cap = want;
+        return OFB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// grow-only pinned host buffer (staging for host-pointer outputs)
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return OFB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            ofb_set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return OFB_E_NOMEM;
+        }
+        cap = want;
+        return OFB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum { OFB_NSCRATCH = 24 };
+
+struct ofb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf scratch[OFB_NSCRATCH];   // role-indexed scratch arenas (see each stage)
+    PinBuf pin[4];
+    std::vector<ofb_pyr*> pyramids;
+    ofb_pyr* pair_pyr[2] = {nullptr, nullptr};   // workspace pyramids of ofb_frame_pairs
+};
+
+// scratch roles
+enum {
+    SC_IN0 = 0, SC_IN1, SC_IN2, SC_IN3, SC_IN4, SC_IN5,      // staged host inputs
+    SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3,                      // staged outputs
+    SC_CAND, SC_CANDCNT, SC_SEL, SC_GRID, SC_PTS0, SC_PTS1, SC_STAT, SC_ERR,
+    SC_MC0, SC_MC1, SC_MC2, SC_TMP0, SC_TMP1, SC_TMP2
+};
+
+struct ofb_pyr {
+    int n_images = 0, n_levels = 0;
+    int w[OFB_MAX_LEVELS], h[OFB_MAX_LEVELS], pitch[OFB_MAX_LEVELS];
+    size_t level_off[OFB_MAX_LEVELS];     // byte offset of level l (image 0) inside `base`
+    size_t image_stride[OFB_MAX_LEVELS];  // byte stride between images at level l
+    uint8_t* base = nullptr;              // owned storage for levels >= 1 (and level 0 when copied)
+    const uint8_t* level0 = nullptr;      // level 0 (may alias caller memory when it was device-resident)
+    int level0_pitch = 0;
+    size_t level0_stride = 0;
+    bool level0_owned = false;
+    size_t bytes = 0;
+};
+
+static inline bool ofb_is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Returns a device view of `p` (bytes long): p itself when device-resident, else a staged copy
+// in scratch[role] (async H2D on the context stream).
+static inline int ofb_stage_in(ofb_ctx* ctx, int role, const void* p, size_t bytes, const void** dev)
+{
+    if (!p || bytes == 0) { *dev = nullptr; return OFB_OK; }
+    if (ofb_is_device_ptr(p)) { *dev = p; return OFB_OK; }
+    OFB_TRY(ctx->scratch[role].reserve(bytes));
+    OFB_CUDA(cudaMemcpyAsync(ctx->scratch[role].p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->scratch[role].p;
+    return OFB_OK;
+}
+
+// Output staging: returns device pointer to write to; remember if a copy-back is needed.
+struct OutStage {
+    void* user = nullptr; void* dev = nullptr; size_t bytes = 0; bool copy_back = false;
+};
+static inline int ofb_stage_out(ofb_ctx* ctx, int role, void* p, size_t bytes, OutStage* o)
+{
+    o->user = p; o->bytes = bytes; o->copy_back = false; o->dev = nullptr;
+    if (!p || bytes == 0) return OFB_OK;
+    if (ofb_is_device_ptr(p)) { o->dev = p; return OFB_OK; }
+    OFB_TRY(ctx->scratch[role].reserve(bytes));
+    o->dev = ctx->scratch[role].p; o->copy_back = true;
+    return OFB_OK;
+}
+// enqueue copy-backs; returns true in *need_sync if any host output was written
+static inline int ofb_finish_out(ofb_ctx* ctx, OutStage* outs, int n)
+{
+    bool any = false;
+    for (int i = 0; i < n; ++i)
+        if (outs[i].copy_back) {
+            OFB_CUDA(cudaMemcpyAsync(outs[i].user, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            any = true;
+        }
+    if (any) OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OFB_OK;
+}
+
+#define OFB_LAUNCH_CHECK(ctx)                                                                   \
+    do { (ctx)->launches++; OFB_CUDA(cudaGetLastError()); } while (0)
+
+static inline int ofb_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// stage entry points implemented in the per-stage translation units (device pointers only)
+int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* pyr);
+int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
+                  int max_level, ofb_pyr** out);
+int ofb_pyr_prepare(ofb_ctx* ctx, ofb_pyr** slot, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
+                    int n_images, int max_level);

@@ -1,0 +1,115 @@
+// pairs.cu -- fused frame-pair path: pyramid -> Shi-Tomasi -> pyramidal LK -> velocity solve for a
+// batch of independent frame pairs, everything enqueued on the context's stream with no host
+// round-trip between stages (feature counts stay on the device).
+//
+// Replaces the per-frame dataflow of velocity_measurment_node:224-267 (centre with of.pix_trans,
+// scale by `scaling`, solve_lgs) and flight_experiments/evaluate_exp.py:77-120
+// (calcOpticalFlowPyrLK -> status filter -> solve_lgs(new_pos, new_pos-old_pos, ...)).
+#include "common.cuh"
+#include "features.cuh"
+#include "pyrlk.cuh"
+#include "velocity_device.cuh"
+
+namespace {
+
+struct TrackLoader {
+    const float* prev; const float* next; const uint8_t* status;
+    const int* counts; int counts_stride; size_t stride;
+    double cx, cy, ps, fs;
+    __device__ int begin(int) const { return 0; }
+    __device__ int end(int f) const { return counts[(size_t)f * counts_stride]; }
+    __device__ bool load(int f, int i, double& px, double& py, double& ux, double& uy) const {
+        size_t o = (size_t)f * stride + i;
+        if (!status[o]) return false;                       // new_pos[status==1]  (node:134, evaluate_exp.py:99)
+        float nx = next[2 * o], ny = next[2 * o + 1];
+        float dx = nx - prev[2 * o], dy = ny - prev[2 * o + 1];   // flow formed in fp32 as cv2 arrays are (node:136)
+        px = ((double)nx - cx) * ps; py = ((double)ny - cy) * ps;  // node:232-233
+        ux = (double)dx * fs; uy = (double)dy * fs;                // node:235
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(OFB_SOLVE_THREADS)
+pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict__ imu, ofb_pair_result* __restrict__ out)
+{
+    int f = blockIdx.x;
+    const ofb_imu_sample& s = imu[f];
+    OfbSolveOut o = ofb_block_solve(ld, f, variant, s.d, s.n, s.w, s.t);
+    if (threadIdx.x == 0) {
+        ofb_pair_result r;
+        for (int k = 0; k < 3; ++k) { r.v[k] = o.v[k]; r.s[k] = o.s[k]; }
+        r.res = o.res; r.rank = o.rank;
+        r.n_features = ld.end(f);
+        r.n_tracked = o.count;
+        out[f] = r;
+    }
+}
+
+}  // namespace
+
+extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pairs,
+                               const uint8_t* prev, const uint8_t* next, int pitch, size_t image_stride,
+                               const ofb_imu_sample* imu, const float* pts_in, const int* n_in,
+                               ofb_pair_result* results, float* prev_pts, float* next_pts, uint8_t* status)
+{
+    OFB_REQUIRE(ctx && cfg && prev && next && imu && results, "frame_pairs: null argument");
+    OFB_REQUIRE(n_pairs > 0 && n_pairs <= 65535, "frame_pairs: n_pairs must be in 1..65535");
+    const int w = cfg->width, h = cfg->height, K = cfg->max_corners;
+    OFB_REQUIRE(w > 0 && h > 0 && pitch >= w, "frame_pairs: bad image geometry");
+    OFB_REQUIRE(K > 0, "frame_pairs: max_corners must be positive");
+    OFB_REQUIRE(cfg->max_level >= 0, "frame_pairs: max_level must be >= 0");
+    OFB_REQUIRE(cfg->variant >= 0 && cfg->variant <= 2, "frame_pairs: unknown variant");
+    OFB_REQUIRE(cfg->detect || (pts_in && n_in), "frame_pairs: detect==0 needs pts_in and n_in");
+    OFB_REQUIRE(n_pairs == 1 || image_stride >= (size_t)pitch * (h - 1) + w, "frame_pairs: image_stride too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    // stage 1: both pyramids (levels >= 1); host frames are copied into the workspace level 0
+    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0], prev, w, h, pitch, image_stride, n_pairs, cfg->max_level));
+    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[1], next, w, h, pitch, image_stride, n_pairs, cfg->max_level));
+    ofb_pyr* pp = ctx->pair_pyr[0];
+    ofb_pyr* pn = ctx->pair_pyr[1];
+    size_t npts = (size_t)n_pairs * K;
+    OutStage o[4];
+    OFB_TRY(ofb_stage_out(ctx, SC_PTS0, prev_pts, sizeof(float) * 2 * npts, &o[0]));
+    OFB_TRY(ofb_stage_out(ctx, SC_PTS1, next_pts, sizeof(float) * 2 * npts, &o[1]));
+    OFB_TRY(ofb_stage_out(ctx, SC_STAT, status, npts, &o[2]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT3, results, sizeof(ofb_pair_result) * n_pairs, &o[3]));
+    // optional outputs still need device storage when the caller passes NULL
+    float* d_prev = (float*)o[0].dev; float* d_next = (float*)o[1].dev; uint8_t* d_stat = (uint8_t*)o[2].dev;
+    if (!d_prev) { OFB_TRY(ctx->scratch[SC_PTS0].reserve(sizeof(float) * 2 * npts)); d_prev = ctx->scratch[SC_PTS0].as<float>(); }
+    if (!d_next) { OFB_TRY(ctx->scratch[SC_PTS1].reserve(sizeof(float) * 2 * npts)); d_next = ctx->scratch[SC_PTS1].as<float>(); }
+    if (!d_stat) { OFB_TRY(ctx->scratch[SC_STAT].reserve(npts)); d_stat = ctx->scratch[SC_STAT].as<uint8_t>(); }
+    const void* dimu;
+    OFB_TRY(ofb_stage_in(ctx, SC_IN3, imu, sizeof(ofb_imu_sample) * n_pairs, &dimu));
+    const int* counts; int counts_stride;
+    if (cfg->detect) {
+        // stage 2 on level 0 of the previous frames
+        FeatImageState* st = nullptr;
+        unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
+        OFB_TRY(ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n_pairs, nullptr, 0, 0, K,
+                                    cfg->quality, cfg->min_distance, cfg->block_size, cand_cap, d_prev, (size_t)2 * K, K,
+                                    &st));
+        counts = &st->n_out; counts_stride = (int)(sizeof(FeatImageState) / sizeof(int));
+    } else {
+        const void *dp, *dn;
+        OFB_TRY(ofb_stage_in(ctx, SC_IN4, n_in, sizeof(int) * n_pairs, &dn));
+        if (ofb_is_device_ptr(pts_in)) {
+            if ((const float*)pts_in != d_prev)
+                OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        (void)dp;
+        counts = (const int*)dn; counts_stride = 1;
+    }
+    // stage 3
+    OFB_TRY(ctx->scratch[SC_ERR].reserve(sizeof(float) * npts));
+    OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, 0, 1, n_pairs, d_prev, counts, counts_stride, K, (size_t)K, cfg->win_w,
+                          cfg->win_h, cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, d_next, d_stat,
+                          ctx->scratch[SC_ERR].as<float>()));
+    // stage 4
+    TrackLoader ld{d_prev, d_next, d_stat, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
+    pair_solve_kernel<<<n_pairs, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, (const ofb_imu_sample*)dimu,
+                                                                     (ofb_pair_result*)o[3].dev);
+    OFB_LAUNCH_CHECK(ctx);
+    return ofb_finish_out(ctx, o, 4);
+}

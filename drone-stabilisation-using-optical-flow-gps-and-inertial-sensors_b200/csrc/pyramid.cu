@@ -1,0 +1,265 @@
+// pyramid.cu -- stage 0/1: BGR->grey and the Gaussian image pyramid.
+//
+// Replaces cv2.cvtColor(COLOR_BGR2GRAY) (velocity_measurment_node:113) and the pyramid that
+// cv2.calcOpticalFlowPyrLK builds internally on every call (velocity_measurment_node:133,
+// flight_experiments/evaluate_exp.py:98, optical_flow_experiments/of_module.py:88): pyrDown =
+// separable [1 4 6 4 1]/16 in both axes, decimate by two, reflect-101 borders, integer
+// (sum + 128) >> 8 -- bit-exact with OpenCV.
+//
+// One CTA produces a 64x16 tile of the destination level for one image of the batch (blockIdx.z).
+// The (2*64+4)x(2*16+3) source footprint is staged once in shared memory with 32-bit coalesced loads
+// (byte loads with reflect-101 index fix-up on border tiles only); every thread then produces four
+// horizontally adjacent outputs from 15 LDS.32 and writes them with one 32-bit store. Source bytes are
+// read from HBM exactly once per level (plus the 4-byte halo), so the kernel is HBM-bound:
+// algorithmic bytes per level = w*h read + ((w+1)/2)*((h+1)/2) written.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT_W = 64, PT_H = 16;                 // output tile
+constexpr int PS_W = 2 * PT_W + 8;                  // staged source columns (word aligned, 4 left + 4 right halo)
+constexpr int PS_H = 2 * PT_H + 3;                  // staged source rows
+constexpr int PS_PITCH = PS_W;                      // bytes, multiple of 4
+
+__device__ __forceinline__ int refl101(int p, int len)
+{
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride,
+                uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride)
+{
+    __shared__ __align__(16) uint8_t tile[PS_H * PS_PITCH];
+    const uint8_t* s = src + (size_t)blockIdx.z * sstride;
+    uint8_t* d = dst + (size_t)blockIdx.z * dstride;
+    int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
+    int sx0 = 2 * X0 - 4, sy0 = 2 * Y0 - 2;         // source coordinate of tile[0][0]
+    bool interior = sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh &&
+                    ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
+    if (interior) {
+        const uint32_t* s32 = (const uint32_t*)(s + (size_t)sy0 * spitch + sx0);
+        int wpitch = spitch >> 2;
+        uint32_t* t32 = (uint32_t*)tile;
+        for (int i = threadIdx.x; i < PS_H * (PS_W / 4); i += 256) {
+            int r = i / (PS_W / 4), c = i - r * (PS_W / 4);
+            t32[r * (PS_PITCH / 4) + c] = __ldg(s32 + (size_t)r * wpitch + c);
+        }
+    } else {
+        for (int i = threadIdx.x; i < PS_H * PS_W; i += 256) {
+            int r = i / PS_W, c = i - r * PS_W;
+            int yy = refl101(sy0 + r, sh), xx = refl101(sx0 + c, sw);
+            tile[r * PS_PITCH + c] = __ldg(s + (size_t)yy * spitch + xx);
+        }
+    }
+    __syncthreads();
+    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 outputs each
+    int ox = X0 + 4 * tx, oy = Y0 + ty;
+    if (ox >= dw || oy >= dh) return;
+    // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8  -> tile columns 8tx+2 .. 8tx+12
+    // read tile columns 8tx .. 8tx+15 (4 words) for rows 2ty .. 2ty+4
+    int col[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) col[c] = 0;
+    const uint32_t* t32 = (const uint32_t*)tile;
+    const int kv[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint32_t* row = t32 + (2 * ty + r) * (PS_PITCH / 4) + 2 * tx;
+        uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+        uint32_t ws[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int c = 0; c < 16; ++c) col[c] += kv[r] * (int)((ws[c >> 2] >> (8 * (c & 3))) & 0xffu);
+    }
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int b = 2 * k + 2;   // tile-local column of source 2(ox+k)-2
+        int v = col[b] + 4 * col[b + 1] + 6 * col[b + 2] + 4 * col[b + 3] + col[b + 4];
+        packed |= (uint32_t)((v + 128) >> 8) << (8 * k);
+    }
+    uint8_t* drow = d + (size_t)oy * dpitch + ox;
+    if (ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0)) {
+        *(uint32_t*)drow = packed;
+    } else {
+        for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
+__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int w, int h, int pitch, uint8_t* __restrict__ gray,
+                                int gpitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* p = bgr + (size_t)y * pitch + 3 * x;
+    gray[(size_t)y * gpitch + x] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + (1 << 14)) >> 15);
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
+{
+    for (int l = 1; l < p->n_levels; ++l) {
+        const uint8_t* s; int sp; size_t ss;
+        if (l == 1) { s = p->level0; sp = p->level0_pitch; ss = p->level0_stride; }
+        else { s = p->base + p->level_off[l - 1]; sp = p->pitch[l - 1]; ss = p->image_stride[l - 1]; }
+        dim3 grid(ofb_div_up(p->w[l], PT_W), ofb_div_up(p->h[l], PT_H), p->n_images);
+        pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss,
+                                                       p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
+                                                       p->image_stride[l]);
+        OFB_LAUNCH_CHECK(ctx);
+    }
+    return OFB_OK;
+}
+
+static int pyr_upload_level0(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* img, int pitch, size_t image_stride)
+{
+    for (int i = 0; i < p->n_images; ++i)
+        OFB_CUDA(cudaMemcpy2DAsync(p->base + p->level_off[0] + (size_t)i * p->image_stride[0], p->pitch[0],
+                                   img + (size_t)i * image_stride, pitch, p->w[0], p->h[0], cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    return OFB_OK;
+}
+
+// Allocates the pyramid object and its level storage. When `img` is device memory level 0 aliases
+// it (the caller keeps it alive while the pyramid is in use); host images are copied in.
+int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
+                  int max_level, ofb_pyr** out)
+{
+    ofb_pyr* p = new ofb_pyr();
+    p->n_images = n_images;
+    bool dev = ofb_is_device_ptr(img);
+    int lw = w, lh = h, nl = 1;
+    p->w[0] = w; p->h[0] = h;
+    for (int l = 1; l <= max_level && l < OFB_MAX_LEVELS; ++l) {
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        p->w[l] = lw; p->h[l] = lh; nl = l + 1;
+        if (lw == 1 && lh == 1) break;
+    }
+    p->n_levels = nl;
+    size_t off = 0;
+    for (int l = 0; l < nl; ++l) {
+        if (l == 0 && dev) { p->pitch[0] = pitch; p->level_off[0] = 0; p->image_stride[0] = image_stride; continue; }
+        p->pitch[l] = (int)align_up((size_t)p->w[l] + 4, 16);
+        p->image_stride[l] = align_up((size_t)p->pitch[l] * p->h[l], 256);
+        p->level_off[l] = off;
+        off += p->image_stride[l] * n_images;
+    }
+    p->bytes = off + 256;
+    cudaError_t e = cudaMalloc((void**)&p->base, p->bytes);
+    if (e != cudaSuccess) {
+        ofb_set_error("pyramid: cudaMalloc(%zu) failed: %s", p->bytes, cudaGetErrorString(e));
+        delete p;
+        return OFB_E_NOMEM;
+    }
+    if (dev) {
+        p->level0 = img; p->level0_pitch = pitch; p->level0_stride = image_stride; p->level0_owned = false;
+    } else {
+        p->level0 = p->base + p->level_off[0]; p->level0_pitch = p->pitch[0]; p->level0_stride = p->image_stride[0];
+        p->level0_owned = true;
+        int r = pyr_upload_level0(ctx, p, img, pitch, image_stride);
+        if (r != OFB_OK) { cudaFree(p->base); delete p; return r; }
+    }
+    *out = p;
+    return OFB_OK;
+}
+
+// Workspace pyramid for the fused path: reuses *slot when geometry and residency match, so a steady
+// stream of frame pairs never reallocates.
+int ofb_pyr_prepare(ofb_ctx* ctx, ofb_pyr** slot, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
+                    int n_images, int max_level)
+{
+    ofb_pyr* p = *slot;
+    bool dev = ofb_is_device_ptr(img);
+    int want_levels = 1; { int lw = w, lh = h; for (int l = 1; l <= max_level && l < OFB_MAX_LEVELS; ++l) { lw = (lw + 1) / 2; lh = (lh + 1) / 2; want_levels = l + 1; if (lw == 1 && lh == 1) break; } }
+    if (p && p->n_images == n_images && p->w[0] == w && p->h[0] == h && p->n_levels == want_levels &&
+        p->level0_owned == !dev) {
+        if (dev) { p->level0 = img; p->level0_pitch = pitch; p->level0_stride = image_stride; p->pitch[0] = pitch; p->image_stride[0] = image_stride; }
+        else OFB_TRY(pyr_upload_level0(ctx, p, img, pitch, image_stride));
+    } else {
+        if (p) { cudaStreamSynchronize(ctx->stream); cudaFree(p->base); delete p; *slot = nullptr; }
+        OFB_TRY(ofb_pyr_alloc(ctx, img, w, h, pitch, image_stride, n_images, max_level, &p));
+        *slot = p;
+    }
+    return ofb_pyr_build_device(ctx, p);
+}
+
+extern "C" int ofb_pyramid(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
+                           int n_images, int max_level, ofb_pyr** out)
+{
+    OFB_REQUIRE(ctx && img && out, "pyramid: null argument");
+    OFB_REQUIRE(w > 0 && h > 0 && pitch >= w, "pyramid: bad image geometry %dx%d pitch %d", w, h, pitch);
+    OFB_REQUIRE(n_images > 0 && n_images <= 65535, "pyramid: n_images must be in 1..65535");
+    OFB_REQUIRE(max_level >= 0, "pyramid: max_level must be >= 0");
+    OFB_REQUIRE(n_images == 1 || image_stride >= (size_t)pitch * (h - 1) + w, "pyramid: image_stride too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    ofb_pyr* p = nullptr;
+    OFB_TRY(ofb_pyr_alloc(ctx, img, w, h, pitch, image_stride, n_images, max_level, &p));
+    int r = ofb_pyr_build_device(ctx, p);
+    if (r != OFB_OK) { cudaFree(p->base); delete p; return r; }
+    ctx->pyramids.push_back(p);
+    *out = p;
+    return OFB_OK;
+}
+
+extern "C" int ofb_pyr_free(ofb_ctx* ctx, ofb_pyr* pyr)
+{
+    OFB_REQUIRE(ctx && pyr, "pyr_free: null argument");
+    for (size_t i = 0; i < ctx->pyramids.size(); ++i)
+        if (ctx->pyramids[i] == pyr) {
+            ctx->pyramids.erase(ctx->pyramids.begin() + i);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(pyr->base);
+            delete pyr;
+            return OFB_OK;
+        }
+    ofb_set_error("pyr_free: pyramid does not belong to this context");
+    return OFB_E_INVALID;
+}
+
+extern "C" int ofb_pyr_info(const ofb_pyr* pyr, int* n_images, int* n_levels, int* widths, int* heights, int* pitches)
+{
+    OFB_REQUIRE(pyr, "pyr_info: null pyramid");
+    if (n_images) *n_images = pyr->n_images;
+    if (n_levels) *n_levels = pyr->n_levels;
+    for (int l = 0; l < pyr->n_levels; ++l) {
+        if (widths) widths[l] = pyr->w[l];
+        if (heights) heights[l] = pyr->h[l];
+        if (pitches) pitches[l] = l == 0 ? pyr->level0_pitch : pyr->pitch[l];
+    }
+    return OFB_OK;
+}
+
+extern "C" int ofb_pyr_download(ofb_ctx* ctx, const ofb_pyr* pyr, int image, int level, uint8_t* dst, int dst_pitch)
+{
+    OFB_REQUIRE(ctx && pyr && dst, "pyr_download: null argument");
+    OFB_REQUIRE(image >= 0 && image < pyr->n_images && level >= 0 && level < pyr->n_levels,
+                "pyr_download: image/level out of range");
+    OFB_REQUIRE(dst_pitch >= pyr->w[level], "pyr_download: dst_pitch too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const uint8_t* s; int sp;
+    if (level == 0) { s = pyr->level0 + (size_t)image * pyr->level0_stride; sp = pyr->level0_pitch; }
+    else { s = pyr->base + pyr->level_off[level] + (size_t)image * pyr->image_stride[level]; sp = pyr->pitch[level]; }
+    OFB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, s, sp, pyr->w[level], pyr->h[level], cudaMemcpyDefault, ctx->stream));
+    OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OFB_OK;
+}
+
+extern "C" int ofb_bgr2gray(ofb_ctx* ctx, const uint8_t* bgr, int w, int h, int pitch, uint8_t* gray, int gray_pitch)
+{
+    OFB_REQUIRE(ctx && bgr && gray, "bgr2gray: null argument");
+    OFB_REQUIRE(w > 0 && h > 0 && pitch >= 3 * w && gray_pitch >= w, "bgr2gray: bad geometry");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const void* din;
+    OFB_TRY(ofb_stage_in(ctx, SC_IN0, bgr, (size_t)pitch * h, &din));
+    OutStage o;
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT0, gray, (size_t)gray_pitch * h, &o));
+    dim3 grid(ofb_div_up(w, 256), h);
+    bgr2gray_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)din, w, h, pitch, (uint8_t*)o.dev, gray_pitch);
+    OFB_LAUNCH_CHECK(ctx);
+    return ofb_finish_out(ctx, &o, 1);
+}

@@ -1,0 +1,311 @@
+// pyrlk.cu -- stage 3: pyramidal Lucas-Kanade tracking, one warp per feature.
+//
+// Replaces cv2.calcOpticalFlowPyrLK(prev, next, prevPts, None, winSize, maxLevel, criteria)
+// (velocity_measurment_node:133; flight_experiments/evaluate_exp.py:98;
+// optical_flow_experiments/of_module.py:88; of_library.py:249). Arithmetic follows OpenCV's
+// lkpyramid.cpp as summarised in SURVEY App. B.3/B.4: Scharr gradients (int16, reflect-101 inside the
+// image, ZERO outside), Q14 fixed-point bilinear patches with 5 fractional bits, fp32 2x2 system,
+// <= maxCount Newton steps with the eps / oscillation exits, L1 patch error at level 0.
+//
+// Mapping: a warp owns one feature for all levels (coarse -> fine) so the whole track is one launch.
+// Per level the (win+3)^2 u8 neighbourhood of I is staged in the warp's shared-memory slice, the
+// Scharr gradients of the (win+1)^2 footprint are formed there once, and the template patch and its
+// two interpolated gradients are kept in shared memory as int16 for the iterations. Each iteration
+// stages the (win+1)^2 window of J (reflect-101 fix-up only for windows that touch the border,
+// a warp-uniform branch), accumulates the mismatch vector in exact int32 per lane, reduces it with
+// 64-bit shuffles and solves the 2x2 system redundantly in every lane's registers. OpenCV builds
+// full-frame Scharr images per level; here gradients are formed only under the windows, so the
+// derivative images (the largest share of OpenCV's LK time) never exist.
+// The kernel is latency/issue bound (dependent iterations), not HBM bound: DESIGN.md, "LK".
+#include "common.cuh"
+#include "pyrlk.cuh"
+
+namespace {
+
+constexpr int LK_WARPS = 4;
+
+__device__ __forceinline__ int refl101(int p, int len)
+{
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Stage the RW x RH block of `img` whose top-left corner is (x0,y0) into dst (row pitch dp),
+// reflect-101 outside the image.
+__device__ __forceinline__ void stage_block(const uint8_t* __restrict__ img, int w, int h, int pitch, int x0, int y0,
+                                            int RW, int RH, uint8_t* dst, int dp, int lane)
+{
+    bool inside = x0 >= 0 && y0 >= 0 && x0 + RW <= w && y0 + RH <= h;
+    if (inside) {
+        const uint8_t* s = img + (size_t)y0 * pitch + x0;
+        for (int r = 0; r < RH; ++r)
+            for (int c = lane; c < RW; c += 32) dst[r * dp + c] = __ldg(s + (size_t)r * pitch + c);
+    } else {
+        for (int r = 0; r < RH; ++r) {
+            const uint8_t* s = img + (size_t)refl101(y0 + r, h) * pitch;
+            for (int c = lane; c < RW; c += 32) dst[r * dp + c] = __ldg(s + refl101(x0 + c, w));
+        }
+    }
+}
+
+__device__ __forceinline__ void bil_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32)
+lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
+                int counts_stride, int n_uniform, size_t pts_stride, size_t warp_smem)
+{
+    extern __shared__ __align__(16) unsigned char lk_smem[];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pair = blockIdx.y;
+    int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
+    int feat = blockIdx.x * LK_WARPS + warp;
+    if (feat >= n) return;
+    const int winW = P.win_w, winH = P.win_h, npx = winW * winH;
+    const int RW = winW + 3, RH = winH + 3, RP = (RW + 3) & ~3;
+    const int DW = winW + 1, DH = winH + 1;
+    unsigned char* base = lk_smem + (size_t)warp * warp_smem;
+    uint8_t* reg = base;                                       // RP x RH staged image bytes
+    short* ders = (short*)(base + (((size_t)RP * RH + 15) & ~(size_t)15));   // Ix, Iy over DW x DH
+    short* pat = ders + 2 * DW * DH;                           // Ipatch, dIx, dIy over npx
+    size_t po = (size_t)pair * pts_stride + feat;
+    float ptx = prev_pts[2 * po], pty = prev_pts[2 * po + 1];
+    float nx = 0.f, ny = 0.f;
+    if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = next_pts[2 * po]; ny = next_pts[2 * po + 1]; }
+    const float hwx = (winW - 1) * 0.5f, hwy = (winH - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    bool st = true;
+    float errv = 0.f;
+    int pimg = P.prev_image0 + pair * P.prev_image_step, nimg = P.next_image0 + pair * P.next_image_step;
+
+    for (int level = P.nlev - 1; level >= 0; --level) {
+        const uint8_t* I = P.prev.base[level] + (size_t)pimg * P.prev.stride[level];
+        const uint8_t* J = P.next.base[level] + (size_t)nimg * P.next.stride[level];
+        const int w = P.prev.w[level], h = P.prev.h[level];
+        const int ipitch = P.prev.pitch[level], jpitch = P.next.pitch[level];
+        float sc = 1.f / (float)(1 << level);
+        float ppx = ptx * sc, ppy = pty * sc;
+        if (level == P.nlev - 1) {
+            if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = nx * sc; ny = ny * sc; }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = nx * 2.f; ny = ny * 2.f; }
+        float px = ppx - hwx, py = ppy - hwy;
+        int ix = __float2int_rd(px), iy = __float2int_rd(py);
+        if (ix < -winW || ix >= w || iy < -winH || iy >= h) {
+            if (level == 0) { st = false; errv = 0.f; }
+            continue;
+        }
+        float a = px - (float)ix, b = py - (float)iy;
+        int w00, w01, w10, w11;
+        bil_weights(a, b, w00, w01, w10, w11);
+        // ---- template: stage I neighbourhood, Scharr under the window, interpolated patches ----
+        __syncwarp();
+        stage_block(I, w, h, ipitch, ix - 1, iy - 1, RW, RH, reg, RP, lane);
+        __syncwarp();
+        for (int i = lane; i < DW * DH; i += 32) {
+            int r = i / DW, c = i - r * DW;
+            int X = ix + c, Y = iy + r;
+            short gx = 0, gy = 0;
+            if ((unsigned)X < (unsigned)w && (unsigned)Y < (unsigned)h) {
+                const uint8_t* r0 = reg + r * RP + c;          // (X-1, Y-1)
+                const uint8_t* r1 = r0 + RP;
+                const uint8_t* r2 = r1 + RP;
+                gx = (short)(3 * ((int)r0[2] - (int)r0[0]) + 10 * ((int)r1[2] - (int)r1[0]) + 3 * ((int)r2[2] - (int)r2[0]));
+                gy = (short)(3 * ((int)r2[0] - (int)r0[0]) + 10 * ((int)r2[1] - (int)r0[1]) + 3 * ((int)r2[2] - (int)r0[2]));
+            }
+            ders[i] = gx; ders[DW * DH + i] = gy;
+        }
+        __syncwarp();
+        int iA11 = 0, iA12 = 0, iA22 = 0;
+        for (int i = lane; i < npx; i += 32) {
+            int y = i / winW, x = i - y * winW;
+            const uint8_t* s0 = reg + (y + 1) * RP + x + 1;
+            const uint8_t* s1 = s0 + RP;
+            int iv = ((int)s0[0] * w00 + (int)s0[1] * w01 + (int)s1[0] * w10 + (int)s1[1] * w11 + (1 << 8)) >> 9;
+            const short* d0 = ders + y * DW + x;
+            const short* d1 = d0 + DW;
+            int gx = ((int)d0[0] * w00 + (int)d0[1] * w01 + (int)d1[0] * w10 + (int)d1[1] * w11 + (1 << 13)) >> 14;
+            const short* e0 = d0 + DW * DH;
+            const short* e1 = e0 + DW;
+            int gy = ((int)e0[0] * w00 + (int)e0[1] * w01 + (int)e1[0] * w10 + (int)e1[1] * w11 + (1 << 13)) >> 14;
+            pat[i] = (short)iv; pat[npx + i] = (short)gx; pat[2 * npx + i] = (short)gy;
+            iA11 += gx * gx; iA12 += gx * gy; iA22 += gy * gy;
+        }
+        float A11 = (float)warp_sum_ll(iA11) * FLT_SCALE;
+        float A12 = (float)warp_sum_ll(iA12) * FLT_SCALE;
+        float A22 = (float)warp_sum_ll(iA22) * FLT_SCALE;
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        float dd = A11 - A22;
+        float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))) /
+                       (float)(2 * winW * winH);
+        if ((double)minEig < P.min_eig_thr || D < 1.1920928955078125e-7f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = 1.f / D;
+        float qx = nx - hwx, qy = ny - hwy;
+        float pdx = 0.f, pdy = 0.f;
+        bool lost = false;
+        for (int j = 0; j < P.max_count; ++j) {
+            int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { lost = true; break; }
+            a = qx - (float)jx; b = qy - (float)jy;
+            bil_weights(a, b, w00, w01, w10, w11);
+            __syncwarp();
+            stage_block(J, w, h, jpitch, jx, jy, DW, DH, reg, RP, lane);
+            __syncwarp();
+            int ib1 = 0, ib2 = 0;
+            for (int i = lane; i < npx; i += 32) {
+                int y = i / winW, x = i - y * winW;
+                const uint8_t* s0 = reg + y * RP + x;
+                const uint8_t* s1 = s0 + RP;
+                int jv = ((int)s0[0] * w00 + (int)s0[1] * w01 + (int)s1[0] * w10 + (int)s1[1] * w11 + (1 << 8)) >> 9;
+                int diff = jv - (int)pat[i];
+                ib1 += diff * (int)pat[npx + i];
+                ib2 += diff * (int)pat[2 * npx + i];
+            }
+            float b1 = (float)warp_sum_ll(ib1) * FLT_SCALE;
+            float b2 = (float)warp_sum_ll(ib2) * FLT_SCALE;
+            float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            qx += dx; qy += dy;
+            nx = qx + hwx; ny = qy + hwy;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (lost && level == 0) st = false;
+        if (st && level == 0) {
+            float rx = nx - hwx, ry = ny - hwy;
+            int jx = __float2int_rd(rx), jy = __float2int_rd(ry);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { st = false; }
+            else {
+                a = rx - (float)jx; b = ry - (float)jy;
+                bil_weights(a, b, w00, w01, w10, w11);
+                __syncwarp();
+                stage_block(J, w, h, jpitch, jx, jy, DW, DH, reg, RP, lane);
+                __syncwarp();
+                int ie = 0;
+                for (int i = lane; i < npx; i += 32) {
+                    int y = i / winW, x = i - y * winW;
+                    const uint8_t* s0 = reg + y * RP + x;
+                    const uint8_t* s1 = s0 + RP;
+                    int jv = ((int)s0[0] * w00 + (int)s0[1] * w01 + (int)s1[0] * w10 + (int)s1[1] * w11 + (1 << 8)) >> 9;
+                    ie += abs(jv - (int)pat[i]);
+                }
+                errv = (float)warp_sum_ll(ie) * (1.f / (float)(32 * winW * winH));
+            }
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
+        status[po] = st ? 1 : 0;
+        if (err) err[po] = st ? errv : 0.f;
+    }
+}
+
+}  // namespace
+
+size_t ofb_lk_warp_smem(int win_w, int win_h)
+{
+    int RW = win_w + 3, RH = win_h + 3, RP = (RW + 3) & ~3;
+    size_t b = (((size_t)RP * RH + 15) & ~(size_t)15);
+    b += sizeof(short) * 2 * (size_t)(win_w + 1) * (win_h + 1) + sizeof(short) * 3 * (size_t)win_w * win_h;
+    return (b + 15) & ~(size_t)15;
+}
+
+static void fill_levels(LKLevelSet* s, const ofb_pyr* p)
+{
+    for (int l = 0; l < p->n_levels; ++l) {
+        if (l == 0) { s->base[0] = p->level0; s->stride[0] = p->level0_stride; s->pitch[0] = p->level0_pitch; }
+        else { s->base[l] = p->base + p->level_off[l]; s->stride[l] = p->image_stride[l]; s->pitch[l] = p->pitch[l]; }
+        s->w[l] = p->w[l]; s->h[l] = p->h[l];
+    }
+}
+
+int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_step, const ofb_pyr* next, int next_image0,
+                  int next_step, int n_pairs, const float* prev_pts, const int* counts, int counts_stride, int n_uniform,
+                  size_t pts_stride, int win_w, int win_h, int max_level, int max_count, double eps, int flags,
+                  double min_eig_thr, float* next_pts, uint8_t* status, float* err)
+{
+    OFB_REQUIRE(win_w > 2 && win_h > 2, "pyrlk: winSize must be larger than 2x2");
+    OFB_REQUIRE(win_w * win_h <= 64 * 64, "pyrlk: winSize too large (max 4096 pixels)");
+    OFB_REQUIRE(prev->w[0] == next->w[0] && prev->h[0] == next->h[0], "pyrlk: prev/next size mismatch");
+    LKParams P;
+    memset(&P, 0, sizeof(P));
+    int nlev = prev->n_levels < next->n_levels ? prev->n_levels : next->n_levels;
+    if (max_level >= 0 && max_level + 1 < nlev) nlev = max_level + 1;
+    // OpenCV cuts the pyramid at the first level that is not larger than the window
+    int eff = 1;
+    for (int l = 1; l < nlev; ++l) {
+        if (prev->w[l] <= win_w || prev->h[l] <= win_h) break;
+        eff = l + 1;
+    }
+    P.nlev = eff;
+    fill_levels(&P.prev, prev);
+    fill_levels(&P.next, next);
+    P.win_w = win_w; P.win_h = win_h;
+    P.max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
+    double e = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
+    P.eps = e * e;
+    P.min_eig_thr = min_eig_thr;
+    P.flags = flags;
+    P.prev_image0 = prev_image0; P.prev_image_step = prev_step;
+    P.next_image0 = next_image0; P.next_image_step = next_step;
+    size_t wsm = ofb_lk_warp_smem(win_w, win_h);
+    size_t smem = wsm * LK_WARPS;
+    static size_t lk_smem_set = 0;
+    if (smem > 48 * 1024 && smem > lk_smem_set) {
+        OFB_CUDA(cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lk_smem_set = smem;
+    }
+    if (n_uniform <= 0) return OFB_OK;
+    dim3 grid(ofb_div_up(n_uniform, LK_WARPS), n_pairs);
+    lk_track_kernel<<<grid, LK_WARPS * 32, smem, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts, counts_stride,
+                                                               n_uniform, pts_stride, wsm);
+    OFB_LAUNCH_CHECK(ctx);
+    return OFB_OK;
+}
+
+extern "C" int ofb_pyrlk(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image, const ofb_pyr* next, int next_image,
+                         const float* prev_pts, int n, int win_w, int win_h, int max_level,
+                         int max_count, double eps, int flags, double min_eig_thr,
+                         float* next_pts, uint8_t* status, float* err)
+{
+    OFB_REQUIRE(ctx && prev && next && next_pts && status, "pyrlk: null argument");
+    OFB_REQUIRE(n >= 0, "pyrlk: negative point count");
+    OFB_REQUIRE(prev_image >= 0 && prev_image < prev->n_images && next_image >= 0 && next_image < next->n_images,
+                "pyrlk: image index out of range");
+    if (n == 0) return OFB_OK;
+    OFB_REQUIRE(prev_pts, "pyrlk: null prevPts");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const void* dpts;
+    OFB_TRY(ofb_stage_in(ctx, SC_PTS0, prev_pts, sizeof(float) * 2 * (size_t)n, &dpts));
+    OutStage o[3];
+    OFB_TRY(ofb_stage_out(ctx, SC_PTS1, next_pts, sizeof(float) * 2 * (size_t)n, &o[0]));
+    OFB_TRY(ofb_stage_out(ctx, SC_STAT, status, (size_t)n, &o[1]));
+    OFB_TRY(ofb_stage_out(ctx, SC_ERR, err, sizeof(float) * (size_t)n, &o[2]));
+    if ((flags & OFB_LK_USE_INITIAL_FLOW) && o[0].copy_back)
+        OFB_CUDA(cudaMemcpyAsync(o[0].dev, next_pts, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    OFB_TRY(ofb_lk_device(ctx, prev, prev_image, 0, next, next_image, 0, 1, (const float*)dpts, nullptr, 0, n, 0, win_w, win_h,
+                          max_level, max_count, eps, flags, min_eig_thr, (float*)o[0].dev, (uint8_t*)o[1].dev,
+                          (float*)o[2].dev));
+    return ofb_finish_out(ctx, o, 3);
+}

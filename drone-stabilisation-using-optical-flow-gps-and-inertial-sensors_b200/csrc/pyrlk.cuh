@@ -1,0 +1,25 @@
+// pyrlk.cuh -- shared declarations of the Lucas-Kanade stage.
+#pragma once
+#include "common.cuh"
+
+struct LKLevelSet {
+    const uint8_t* base[OFB_MAX_LEVELS];
+    unsigned long long stride[OFB_MAX_LEVELS];   // bytes between images of the batch at this level
+    int w[OFB_MAX_LEVELS], h[OFB_MAX_LEVELS], pitch[OFB_MAX_LEVELS];
+};
+
+struct LKParams {
+    LKLevelSet prev, next;
+    int nlev;                     // levels actually used (after OpenCV's window-size cut)
+    int win_w, win_h, max_count, flags;
+    double eps;                   // squared, clamped
+    double min_eig_thr;
+    int prev_image0, prev_image_step, next_image0, next_image_step;   // image of pair p = image0 + p*step
+};
+
+// Device-pointer core. counts (optional): per-pair feature count at counts[pair*counts_stride];
+// n_uniform = upper bound of the per-pair count (grid size).
+int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_step, const ofb_pyr* next, int next_image0,
+                  int next_step, int n_pairs, const float* prev_pts, const int* counts, int counts_stride, int n_uniform,
+                  size_t pts_stride, int win_w, int win_h, int max_level, int max_count, double eps, int flags,
+                  double min_eig_thr, float* next_pts, uint8_t* status, float* err);

@@ -1,0 +1,358 @@
+"""Stage 5 host mirror of numerical_simulation/simulation.py: the Monte-Carlo error propagation.
+
+Same positional signatures as the reference:
+    of_simulation(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, pos,
+                  ang_vel_sig, translation_sig, height_sig, flow_sig, position_sig, normal_sig)
+        simulation.py:36-66  -> (v_obs (iterations,3), feasible (2,N), R (iterations,))
+    feas_simulation(..., normal_sigi, true_vel)      simulation.py:70-104 -> six (N,) per-point means
+    overlap(data1, data2)                             simulation.py:124-136
+The reference reads `iterations` and `true_flow` (and, in feas_simulation, `normal_sig`,
+`velocity_sig`) from module globals; the same names exist here as module attributes and can also be
+passed as keywords. The sweep drivers (simulation.py:183-578) are `SWEEPS[name]` /
+`run_named_sweep`, which return the flat arrays the reference np.save()s.
+
+All trials run on the GPU (libofb200.so, Philox4x32-10 counter RNG); only per-step sums come back.
+Sharded runs (`run_sweep(..., group=...)`) give each rank a contiguous trial range and merge the
+sums with one tiny all-reduce, so the statistics equal a single-GPU run up to fp64 summation order.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import velocity as _vel
+
+# ---- reference constants (simulation.py:154-178) ------------------------------------------------
+linear_velocity = np.array([1.0, 1.0, 1.0])
+angular_velocity = np.array([1.0, 1.0, 1.0])
+height_above_gr = 1.0
+normal_vector = np.array([0.0, 0.0, 1.0])
+translation = np.array([0.02, 0.0, 0.205])
+ang_vel_sig = 0.00071
+translation_sig = 0.005
+height_sig = 0.01
+flow_sig = 0.056 * np.sqrt(2) * 1.23
+position_sig = 0.056 * 1.23
+normal_sig = 0.00065
+velocity_sig = 0.01
+iterations = 100
+true_flow = None          # set by the caller like the reference's global, or passed as keyword
+seed = 0                  # RNG key for of_simulation / feas_simulation calls without an explicit seed
+_call_counter = [0]       # successive calls draw from disjoint Philox streams (step ids)
+
+PRECISIONS = {"fp32": 0, "fp64": 1}
+
+
+def _v3(a):
+    return np.asarray(a, dtype=np.float64).reshape(3)
+
+
+def make_step(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, n_points, pos_offset,
+              ang_vel_sig, translation_sig, height_sig, flow_sig, position_sig, normal_sig, velocity_sig=0.0,
+              true_vel=(0.0, 0.0, 0.0)):
+    s = _lib.McStep()
+    s.v[:] = _v3(linear_velocity); s.w[:] = _v3(angular_velocity); s.n[:] = _v3(normal_vector); s.t[:] = _v3(translation)
+    s.height = float(np.asarray(height_above_gr, dtype=np.float64).reshape(-1)[0])
+    if s.height == 0.0:
+        raise ValueError("height_above_gr must be non-zero")
+    for name, val in (("ang_vel_sig", ang_vel_sig), ("translation_sig", translation_sig), ("height_sig", height_sig),
+                      ("flow_sig", flow_sig), ("position_sig", position_sig), ("normal_sig", normal_sig),
+                      ("velocity_sig", velocity_sig)):
+        val = float(val)
+        if val < 0:
+            raise ValueError("%s must be >= 0 (numpy.random.normal rejects negative scales)" % name)
+        setattr(s, name, val)
+    s.true_vel[:] = _v3(true_vel)
+    s.n_points = int(n_points)
+    s.pos_offset = int(pos_offset)
+    return s
+
+
+def _steps_array(steps):
+    arr = (_lib.McStep * len(steps))()
+    for i, s in enumerate(steps):
+        C.memmove(C.byref(arr, i * C.sizeof(_lib.McStep)), C.byref(s), C.sizeof(_lib.McStep))
+    return arr
+
+
+def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, precision="fp32", dump=False, ctx=None):
+    """Run `trials` trials of every step on this GPU. Returns the per-step sums (structured array
+    _lib.MCSUMS_DTYPE) and, when dump, v_obs (S,trials,3) and R (S,trials)."""
+    ctx = ctx or _lib.default_context()
+    trials = int(trials)
+    if trials <= 0:
+        raise ValueError(' iterations must be a positive number')
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    flow = np.ascontiguousarray(flow, dtype=np.float64).reshape(-1, 2)
+    if pos.shape != flow.shape:
+        raise ValueError("pos and true_flow must have the same shape")
+    arr = _steps_array(steps)
+    sums = np.zeros(len(steps), _lib.MCSUMS_DTYPE)
+    vd = Rd = None
+    if dump:
+        vd = np.zeros((len(steps), trials, 3))
+        Rd = np.zeros((len(steps), trials))
+    _lib.check(ctx.lib.ofb_mc_sweep(ctx.h, C.cast(arr, C.c_void_p), len(steps), int(step_id_base), _lib.ptr(pos),
+                                    _lib.ptr(flow), len(pos), int(trial_begin), trials, int(seed) & (2 ** 64 - 1),
+                                    PRECISIONS[precision], _lib.ptr(sums), _lib.ptr(vd), _lib.ptr(Rd)))
+    if dump:
+        return sums, vd, Rd
+    return sums
+
+
+def shard_range(total, rank, world):
+    """Contiguous trial range of `rank`: [begin, begin+count)."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def merge_sums(sums, group=None, device=None):
+    """All-reduce(sum) of the per-step sums over a torch.distributed group (NCCL on CUDA tensors,
+    gloo on CPU tensors). The message is 8 doubles per step."""
+    import torch
+    import torch.distributed as dist
+    flat = np.ascontiguousarray(sums).view(np.float64).reshape(len(sums), 8)
+    t = torch.from_numpy(flat.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    out = t.cpu().numpy().reshape(-1).view(_lib.MCSUMS_DTYPE)
+    return out.copy()
+
+
+def stats_from_sums(sums, steps):
+    """mean (S,3), population std (S,3) (np.std, ddof=0, as simulation.py:197-200), mean R (S,), n (S,)."""
+    n = sums["n"]
+    vt = np.array([[s.v[0], s.v[1], s.v[2]] for s in steps])
+    md = sums["sum_dv"] / n[:, None]
+    mean = vt + md
+    var = sums["sum_dv2"] / n[:, None] - md ** 2
+    std = np.sqrt(np.maximum(var, 0.0))
+    return mean, std, sums["sum_R"] / n, n
+
+
+def run_sweep(steps, pos, flow, trials, seed=0, precision="fp32", distributed=False, group=None, ctx=None):
+    """Run a sweep; with distributed=True the trials are sharded over the torch.distributed ranks and
+    the sums merged. Returns (mean, std, meanR, n)."""
+    if distributed:
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        begin, count = shard_range(trials, rank, world)
+        if count > 0:
+            sums = run_steps(steps, pos, flow, count, seed=seed, trial_begin=begin, precision=precision, ctx=ctx)
+        else:
+            sums = np.zeros(len(steps), _lib.MCSUMS_DTYPE)
+        dev = torch.device("cuda", (ctx or _lib.default_context()).device) if dist.get_backend(group) == "nccl" else None
+        sums = merge_sums(sums, group, dev)
+    else:
+        sums = run_steps(steps, pos, flow, trials, seed=seed, precision=precision, ctx=ctx)
+    return stats_from_sums(sums, steps)
+
+
+# ---- reference-signature functions ----------------------------------------------------------------
+def _philox_normals(seed, step, trial, n_blocks):
+    """Host replay of the device's draws for ONE trial (used only to rebuild the `feasible` by-product
+    that of_simulation returns for its last trial, simulation.py:65)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    out = np.zeros((n_blocks, 4))
+    for b in range(n_blocks):
+        c = [trial & 0xFFFFFFFF, (trial >> 32) & 0xFFFFFFFF, b, step & 0xFFFFFFFF]
+        k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF,
+                 p0 & 0xFFFFFFFF]
+            k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+        u = [float((np.float32(x) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)) for x in c]
+        for h in (0, 1):
+            rad = np.sqrt(-2.0 * np.log(u[2 * h]))
+            ang = 2.0 * np.pi * (u[2 * h + 1] - 0.5)
+            out[b, 2 * h], out[b, 2 * h + 1] = rad * np.cos(ang), rad * np.sin(ang)
+    return out
+
+
+def of_simulation(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, pos, ang_vel_sig,
+                  translation_sig, height_sig, flow_sig, position_sig, normal_sig, *, iterations=None, true_flow=None,
+                  seed=None, step_id=None, precision="fp32", ctx=None):
+    g = globals()
+    iters = int(g["iterations"] if iterations is None else iterations)
+    if iters <= 0:
+        raise ValueError(' iterations must be a positive number')
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    tf = g["true_flow"] if true_flow is None else true_flow
+    if tf is None:
+        tf = _vel.generate_test_data(pos, linear_velocity, angular_velocity, height_above_gr, normal_vector, translation,
+                                     ctx=ctx)
+    tf = np.ascontiguousarray(tf, dtype=np.float64).reshape(-1, 2)
+    sd = int(g["seed"] if seed is None else seed)
+    if step_id is None:
+        step_id = _call_counter[0]
+        _call_counter[0] += 1
+    step = make_step(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, len(pos), 0,
+                     ang_vel_sig, translation_sig, height_sig, flow_sig, position_sig, normal_sig)
+    _, v_obs, R = run_steps([step], pos, tf, iters, seed=sd, step_id_base=step_id, precision=precision, dump=True, ctx=ctx)
+    # `feasible` is the LAST trial's (simulation.py:65): rebuild that trial's noisy inputs on the host
+    z = _philox_normals(sd, step_id, iters - 1, 3 + len(pos))
+    w_err = _v3(angular_velocity) + ang_vel_sig * z[0, :3]
+    t_err = _v3(translation) + translation_sig * z[1, :3]
+    flow_err = tf + flow_sig * z[3:, 0:2]
+    pos_err = pos + position_sig * z[3:, 2:4]
+    n_err = _v3(normal_vector) / np.linalg.norm(_v3(normal_vector))
+    feasible = _vel.feasibility(pos_err, linear_velocity, flow_err, w_err, t_err, n_err, ctx=ctx)
+    return v_obs[0], feasible, R[0]
+
+
+def feas_simulation(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, pos, ang_vel_sig,
+                    translation_sig, height_sig, flow_sig, position_sig, normal_sigi, true_vel, *, iterations=None,
+                    true_flow=None, seed=None, step_id=None, normal_sig=None, velocity_sig=None, trial_begin=0, ctx=None,
+                    return_sums=False):
+    """simulation.py:70-104. `normal_sigi` is ignored exactly as in the reference (the global normal_sig
+    is what perturbs the normal, lines 87-88); pass normal_sig= to override the module attribute."""
+    ctx = ctx or _lib.default_context()
+    g = globals()
+    iters = int(g["iterations"] if iterations is None else iterations)
+    if iters <= 0:
+        raise ValueError(' iterations must be a positive number')
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    tf = g["true_flow"] if true_flow is None else true_flow
+    if tf is None:
+        raise ValueError("feas_simulation needs true_flow (module attribute or keyword), as the reference's global")
+    tf = np.ascontiguousarray(tf, dtype=np.float64).reshape(-1, 2)
+    if len(tf) != len(pos):
+        raise ValueError("true_flow and pos must have the same number of points")   # reference hard-codes 200 (sim:83-84)
+    sd = int(g["seed"] if seed is None else seed)
+    if step_id is None:
+        step_id = _call_counter[0]
+        _call_counter[0] += 1
+    step = make_step(linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, len(pos), 0,
+                     ang_vel_sig, translation_sig, height_sig, flow_sig, position_sig,
+                     g["normal_sig"] if normal_sig is None else normal_sig,
+                     g["velocity_sig"] if velocity_sig is None else velocity_sig, true_vel)
+    sums = np.zeros((6, len(pos)))
+    _lib.check(ctx.lib.ofb_mc_feas(ctx.h, C.cast(C.byref(step), C.c_void_p), int(step_id), _lib.ptr(pos), _lib.ptr(tf),
+                                   int(trial_begin), iters, sd & (2 ** 64 - 1), _lib.ptr(sums)))
+    if return_sums:
+        return sums
+    m = sums / iters
+    return m[0], m[1], m[2], m[3], m[4], m[5]
+
+
+def overlap(data1, data2, ctx=None):
+    """simulation.py:124-136: common 100-bin histogram over the pooled range, sum of bin-wise minima."""
+    ctx = ctx or _lib.default_context()
+    d1 = np.ascontiguousarray(data1, dtype=np.float64).reshape(-1)
+    d2 = np.ascontiguousarray(data2, dtype=np.float64).reshape(-1)
+    los, his = [], []
+    for d in (d1, d2):
+        if len(d):
+            lo, hi = C.c_double(), C.c_double()
+            _lib.check(ctx.lib.ofb_minmax(ctx.h, _lib.ptr(d), len(d), C.byref(lo), C.byref(hi)))
+            los.append(lo.value); his.append(hi.value)
+    if not los:
+        return 0
+    lo, hi = min(los), max(his)
+    hists = []
+    for d in (d1, d2):
+        cnt = np.zeros(100, np.uint64)
+        if len(d):
+            _lib.check(ctx.lib.ofb_histogram(ctx.h, _lib.ptr(d), len(d), lo, hi, 100, _lib.ptr(cnt)))
+        hists.append(cnt)
+    return int(np.sum(np.minimum(hists[0], hists[1])))
+
+
+# ---- sweep drivers (simulation.py:183-578) ------------------------------------------
+def centred_points(data, fx=1.27, fy=0.93):
+    """simulation.py:186-187: x=(x-mean)*1.27, y=(y-mean)*0.93."""
+    d = np.array(data, dtype=np.float64)
+    d[:, 0] = (d[:, 0] - np.mean(d[:, 0])) * fx
+    d[:, 1] = (d[:, 1] - np.mean(d[:, 1])) * fy
+    return d
+
+
+def miscentred_points(data, fx=1.27, fy=0.93):
+    """simulation.py:442-443 / 552-553: the precedence slip `x - mean*1.27` of two sweeps, kept."""
+    d = np.array(data, dtype=np.float64)
+    d[:, 0] = d[:, 0] - np.mean(d[:, 0]) * fx
+    d[:, 1] = d[:, 1] - np.mean(d[:, 1]) * fy
+    return d
+
+
+def _default_sigmas():
+    g = globals()
+    return dict(ang_vel_sig=g["ang_vel_sig"], translation_sig=g["translation_sig"], height_sig=g["height_sig"],
+                flow_sig=g["flow_sig"], position_sig=g["position_sig"], normal_sig=g["normal_sig"])
+
+
+def build_sweep(name, data, k=None):
+    """Steps, point array and true flow of a named sweep. `data` is the (N,2) point set (points.txt)."""
+    g = globals()
+    v, w, h, n, t = g["linear_velocity"], g["angular_velocity"], g["height_above_gr"], g["normal_vector"], g["translation"]
+    steps, pts, flows = [], [], []
+
+    def add(points, height=h, normal=n, **over):
+        sig = _default_sigmas()
+        sig.update(over)
+        off = sum(len(p) for p in pts)
+        pts.append(points)
+        flows.append(_vel.generate_test_data(points, v, w, height, normal, t))
+        steps.append(make_step(v, w, height, normal, t, len(points), off, **sig))
+
+    if name == "flow_errors":                 # simulation.py:183-202
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, flow_sig=0.001 * i, position_sig=np.sqrt(2) / 1000 * i)
+    elif name == "distance_error":            # 216-235
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, height_sig=0.001 * i)
+    elif name == "ang_vel_error":             # 249-271
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, ang_vel_sig=0.001 * i)
+    elif name == "normal_error":              # 285-304 (no effect: SURVEY App. D.1)
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, normal_sig=0.001 * i)
+    elif name == "translation_error":         # 319-338
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, translation_sig=0.001 * i)
+    elif name == "orientation":               # 357-377
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, normal=np.array([np.sin(np.pi * i / k), 0.0, np.cos(np.pi * i / k)]))
+    elif name == "height":                    # 401-423
+        k = k or 100; d = centred_points(data)
+        for i in range(k):
+            add(d, height=0.2 + np.linspace(0.2, 7.65, k)[i])
+    elif name == "point_position":            # 442-461
+        k = k or 100; d = miscentred_points(data)
+        for i in range(k):
+            add(d + np.ones_like(d) * i / 100)
+    elif name == "number_of_points":          # 552-578
+        k = k or 99; d = miscentred_points(data)
+        for i in range(k):
+            add(d[:2 * i + 2])
+    else:
+        raise ValueError("unknown sweep %r" % name)
+    return steps, np.vstack(pts), np.vstack(flows)
+
+
+SWEEPS = ("flow_errors", "distance_error", "ang_vel_error", "normal_error", "translation_error", "orientation", "height",
+          "point_position", "number_of_points")
+SWEEP_FILES = {"flow_errors": "effect_of_flow_errors", "distance_error": "effect_of_distance_error",
+               "ang_vel_error": "effect_o_ang_vel_error", "normal_error": "effect_of_normal_error",
+               "translation_error": "effect_of_translation_error", "orientation": "effect_of_orientation",
+               "height": "effect_of_height", "point_position": "effect_of_point_position",
+               "number_of_points": "number_of_point"}
+
+
+def run_named_sweep(name, data, trials=100, k=None, seed=0, precision="fp32", distributed=False, group=None, ctx=None):
+    """-> (flat, meanR): flat = np.append(v_flow, v_flow_err), the array the reference saves
+    (layout [means (3k) | stds (3k)], numerical_simulation/visualisation.py:5-14)."""
+    steps, pts, flows = build_sweep(name, data, k)
+    mean, std, mR, _ = run_sweep(steps, pts, flows, trials, seed=seed, precision=precision, distributed=distributed,
+                                 group=group, ctx=ctx)
+    return np.append(mean, std), mR

@@ -1,0 +1,229 @@
+/*
+ * ofb200.h -- C ABI of libofb200.so: the B200 (sm_100a) velocity-measurement hot path.
+ *
+ * The reference (liquidcronos/Drone-stabilisation-using-Optical-Flow-Gps-and-Inertial-Sensors)
+ * is pure Python and has no FFI layer; the boundary it offers is the set of Python call shapes
+ * its drivers use. Each entry point below names the reference call it replaces
+ * (paths relative to the reference checkout). The Python mirror of those call shapes lives in
+ * drone-stabilisation-using-optical-flow-gps-and-inertial-sensors_b200/ and binds these symbols
+ * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error (OFB_E_*); ofb_last_error() returns the
+ *    message of the calling thread's last failure. No exception crosses the boundary.
+ *  - pointer arguments may be HOST or DEVICE memory; the library classifies each pointer with
+ *    cudaPointerGetAttributes. Host inputs are copied in, host outputs copied out, on the
+ *    context's stream; a call with any host OUTPUT returns after that output is complete.
+ *    Calls whose outputs are all device-resident return after enqueueing (use ofb_ctx_sync).
+ *  - a context = one CUDA device + one stream + grow-only scratch arenas. Not thread-safe per
+ *    context; contexts are independent (one per camera stream / callback thread).
+ *  - images are 8-bit single channel, row pitch in bytes.
+ */
+#ifndef OFB200_H
+#define OFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_OK            0
+#define OFB_E_INVALID    -1   /* bad argument (Python layer raises ValueError) */
+#define OFB_E_CUDA       -2   /* CUDA runtime failure */
+#define OFB_E_NOMEM      -3
+#define OFB_E_UNSUPPORTED -4
+
+#define OFB_MAX_LEVELS   16
+
+typedef struct ofb_ctx ofb_ctx;
+typedef struct ofb_pyr ofb_pyr;
+
+const char* ofb_last_error(void);
+int  ofb_version(void);
+
+/* ---- context ----------------------------------------------------------------------------- */
+int ofb_ctx_create(int device, ofb_ctx** out);
+/* same, but all work is enqueued on an existing cudaStream_t (e.g. torch's current stream) */
+int ofb_ctx_create_on_stream(int device, void* cuda_stream, ofb_ctx** out);
+int ofb_ctx_destroy(ofb_ctx* ctx);
+int ofb_ctx_sync(ofb_ctx* ctx);
+int ofb_ctx_stream(ofb_ctx* ctx, void** cuda_stream_out);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int ofb_ctx_launch_count(ofb_ctx* ctx, uint64_t* out);
+/* CUDA-event bracket on the context's stream: ofb_timer_start, ..., ofb_timer_stop -> ms */
+int ofb_timer_start(ofb_ctx* ctx);
+int ofb_timer_stop(ofb_ctx* ctx, float* ms_out);
+/* device scratch for callers that want resident inputs without torch: plain cudaMalloc/cudaFree,
+ * host<->device copies on the context's stream */
+int ofb_dev_alloc(ofb_ctx* ctx, size_t bytes, void** out);
+int ofb_dev_free(ofb_ctx* ctx, void* p);
+int ofb_host_alloc_pinned(ofb_ctx* ctx, size_t bytes, void** out);
+int ofb_host_free_pinned(ofb_ctx* ctx, void* p);
+int ofb_memcpy(ofb_ctx* ctx, void* dst, const void* src, size_t bytes);   /* direction inferred; synchronous */
+int ofb_memcpy_async(ofb_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- stage 0: BGR -> grey. Replaces cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+ *      velocity_measurment_node:113, flight_experiments/evaluate_exp.py:65,85,
+ *      optical_flow_experiments/of_module.py:40,80.  (3735 B + 19235 G + 9798 R + 2^14) >> 15 */
+int ofb_bgr2gray(ofb_ctx* ctx, const uint8_t* bgr, int w, int h, int pitch, uint8_t* gray, int gray_pitch);
+
+/* ---- stage 1: Gaussian pyramid. Replaces the pyramid built inside cv2.calcOpticalFlowPyrLK
+ *      (velocity_measurment_node:133, evaluate_exp.py:98, of_module.py:88, of_library.py:249);
+ *      same arithmetic as cv2.pyrDown: [1 4 6 4 1]^2, reflect-101, (sum+128)>>8.
+ *      n_images images of identical size, image i at img + i*image_stride. Level l of image i is
+ *      ((w+1)/2^l...) as in OpenCV. The pyramid is owned by the context until ofb_pyr_free. */
+int ofb_pyramid(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
+                int n_images, int max_level, ofb_pyr** out);
+int ofb_pyr_free(ofb_ctx* ctx, ofb_pyr* pyr);
+int ofb_pyr_info(const ofb_pyr* pyr, int* n_images, int* n_levels, int* widths, int* heights, int* pitches);
+/* copy level `level` of image `image` to dst (host or device), dst_pitch bytes per row */
+int ofb_pyr_download(ofb_ctx* ctx, const ofb_pyr* pyr, int image, int level, uint8_t* dst, int dst_pitch);
+
+/* ---- stage 2: Shi-Tomasi. Replaces cv2.goodFeaturesToTrack(gray, mask=..., maxCorners,
+ *      qualityLevel, minDistance, blockSize)  velocity_measurment_node:120,163,
+ *      evaluate_exp.py:66,106, of_module.py:44,86, of_library.py:238.
+ *      xy_out: capacity `capacity` points (x,y float32, integer valued); *n_out = number found
+ *      (cv2 returns None when 0). max_corners <= 0 means "all" (as in cv2). */
+int ofb_good_features(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch,
+                      const uint8_t* mask, int mask_pitch,
+                      int max_corners, double quality, double min_distance, int block_size,
+                      float* xy_out, int capacity, int* n_out);
+/* the lambda_min map itself (cv2.cornerMinEigenVal(gray, blockSize)); eig_out is w*h float32 */
+int ofb_min_eig_map(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, int block_size, float* eig_out);
+
+/* ---- stage 3: pyramidal Lucas-Kanade. Replaces cv2.calcOpticalFlowPyrLK(prev, next, prevPts,
+ *      None, winSize, maxLevel, criteria)  (same call sites as stage 1).
+ *      prev/next: pyramids from ofb_pyramid; image index selects the image inside each pyramid.
+ *      max_level < 0 uses every level of the pyramid; levels whose size is <= the window are cut
+ *      as in OpenCV. criteria: max_count (clamped to [0,100]) and eps (clamped to [0,10]).
+ *      flags: OFB_LK_USE_INITIAL_FLOW (next_pts holds the initial guess). */
+#define OFB_LK_USE_INITIAL_FLOW 4
+int ofb_pyrlk(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image, const ofb_pyr* next, int next_image,
+              const float* prev_pts, int n, int win_w, int win_h, int max_level,
+              int max_count, double eps, int flags, double min_eig_thr,
+              float* next_pts, uint8_t* status, float* err);
+
+/* ---- stage 4: planar-flow velocity least squares. Replaces solve_lgs
+ *      variant OFB_VARIANT_NODE  velocity_measurment_node:30-42   (x,u,d,n,omega)
+ *      variant OFB_VARIANT_EXP   flight_experiments/evaluate_exp.py:18-31 (x,u,d,n,omega,t)
+ *      variant OFB_VARIANT_SIM   numerical_simulation/simulation.py:15-30 (x,u,d,n,omega,t)
+ *      x,u: n x 2 float64 (metric). Outputs: v[3]; res[1] (sum of squared residuals; valid only
+ *      when *rank==3 and 3n>3, as np.linalg.lstsq); rank; s[3] singular values (descending).
+ *      Batched form: n_frames problems, problem f uses points [offsets[f], offsets[f+1]). */
+#define OFB_VARIANT_NODE 0
+#define OFB_VARIANT_EXP  1
+#define OFB_VARIANT_SIM  2
+int ofb_solve_velocity(ofb_ctx* ctx, int variant, const double* x, const double* u, int n, double d,
+                       const double n3[3], const double w3[3], const double t3[3],
+                       double v_out[3], double* res, int* rank, double s_out[3]);
+int ofb_solve_velocity_batched(ofb_ctx* ctx, int variant, const double* x, const double* u,
+                               const int* offsets, int n_frames,
+                               const double* d, const double* n3, const double* w3, const double* t3,
+                               double* v_out, double* res, int* rank, double* s_out);
+/* generate_test_data: simulation.py:7-12 (t3 != NULL) / velocity_measurment_node:25-29 (t3 NULL) */
+int ofb_generate_flow(ofb_ctx* ctx, const double* x, int n, const double v3[3], const double w3[3],
+                      double d, const double n3[3], const double* t3, double* u_out);
+/* r_tilde: of_library.py:365-386. x,u are n x ld doubles (ld = 2, or 3 for the homogeneous 4-arg
+ * copy in sensor_precision_experiments/pixhawk_pure_IMU/of_library.py:365-384, then dist is ignored
+ * when <= 0). Outputs r[n], d_out[n]. */
+int ofb_r_tilde(ofb_ctx* ctx, const double* x, const double* u, int n, int ld, const double n3[3],
+                const double v3[3], double dist, double* r_out, double* d_out);
+/* feasibility: simulation.py:108-120 -> out[2*n] = parallelity[n] then length[n] */
+int ofb_feasibility(ofb_ctx* ctx, const double* x, const double* v3, const double* u, int n,
+                    const double w3[3], const double t3[3], const double n3[3], double* out);
+
+/* ---- fused frame pairs (stages 1-4): what velocity_measurment_node:224-267 and
+ *      evaluate_exp.py:77-120 do per frame: detect on prev, track into next, convert pixel
+ *      positions/flows to metric, solve. n_pairs independent pairs, images of identical size. */
+typedef struct {
+    int    width, height;
+    int    max_level;                 /* LK maxLevel (levels = max_level+1 before the cut) */
+    int    max_corners;               /* > 0 */
+    double quality, min_distance;
+    int    block_size;
+    int    win_w, win_h, max_count;
+    double eps, min_eig_thr;
+    int    variant;                   /* OFB_VARIANT_* */
+    double cx, cy;                    /* principal point (of.pix_trans) */
+    double pos_scale;                 /* x = (p_new - c) * pos_scale     node:229-233 */
+    double flow_scale;                /* u = (p_new - p_old) * flow_scale  node:235 */
+    int    detect;                    /* 1: detect on prev (detect+track+solve); 0: use pts_in */
+} ofb_pair_cfg;
+
+typedef struct {   /* per pair IMU/sonar sample */
+    double d;        /* height above ground */
+    double n[3];     /* plane normal (third column of R) */
+    double w[3];     /* gyro rate */
+    double t[3];     /* lever arm (EXP/SIM variants) */
+} ofb_imu_sample;
+
+typedef struct {
+    double v[3];
+    double s[3];
+    double res;
+    int    rank;
+    int    n_features;   /* detected (or given) */
+    int    n_tracked;    /* status==1 */
+} ofb_pair_result;
+
+/* prev/next: n_pairs images each, image i at base + i*image_stride (host or device).
+ * pts_in (detect==0): n_pairs x max_corners x 2 float32 with counts n_in[n_pairs].
+ * Optional outputs (may be NULL): prev_pts/next_pts (n_pairs x max_corners x 2 f32),
+ * status (n_pairs x max_corners u8). */
+int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pairs,
+                    const uint8_t* prev, const uint8_t* next, int pitch, size_t image_stride,
+                    const ofb_imu_sample* imu, const float* pts_in, const int* n_in,
+                    ofb_pair_result* results, float* prev_pts, float* next_pts, uint8_t* status);
+
+/* ---- stage 5: Monte-Carlo error propagation. Replaces of_simulation (simulation.py:36-66),
+ *      feas_simulation (simulation.py:70-104) and the per-step np.mean/np.std of the sweep
+ *      drivers (e.g. simulation.py:183-202). One ofb_mc_step = one call of of_simulation. */
+#define OFB_MC_MAX_POINTS 256
+typedef struct {
+    double v[3], w[3], n[3], t[3];       /* truth: linear/angular velocity, normal, lever arm */
+    double height;
+    double ang_vel_sig, translation_sig, height_sig, flow_sig, position_sig, normal_sig;
+    double velocity_sig;                 /* feas_simulation only (global at simulation.py:172) */
+    double true_vel[3];                  /* feas_simulation only */
+    int    n_points;
+    int    pos_offset;                   /* index (in points) of this step's first point in pos/flow */
+} ofb_mc_step;
+
+typedef struct {                         /* per step, sums over trials (mergeable across shards) */
+    double n;                            /* trials accumulated */
+    double sum_dv[3];                    /* sum (v_obs - v_true) */
+    double sum_dv2[3];                   /* sum (v_obs - v_true)^2 */
+    double sum_R;                        /* sum of the analytic bound R */
+} ofb_mc_sums;
+
+/* pos / true_flow: all steps' points, (total_points x 2) float64. Trials [trial_begin,
+ * trial_begin+trials) of every step are run; RNG = Philox4x32-10 keyed by seed with counter
+ * (trial id, draw block, step id + step_id_base) so any sharding of the trial range reproduces
+ * the same union. sums_out: n_steps entries (host or device), OVERWRITTEN. Optional dumps (may
+ * be NULL; device or host): v_dump (n_steps x trials x 3), R_dump (n_steps x trials).
+ * precision: 0 = fp32 per-point arithmetic with fp64 accumulation, 1 = fp64 throughout. */
+int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps, int step_id_base,
+                 const double* pos, const double* true_flow, int total_points,
+                 uint64_t trial_begin, uint64_t trials, uint64_t seed, int precision,
+                 ofb_mc_sums* sums_out, double* v_dump, double* R_dump);
+
+/* feas_simulation: per-point sums over trials of the six quantities returned at
+ * simulation.py:104 (backward par, backward dist, forward par, forward dist, backward res,
+ * forward res): sums_out[6*n_points] (+ n in *n_out); means = sums / n. */
+int ofb_mc_feas(ofb_ctx* ctx, const ofb_mc_step* step, int step_id,
+                const double* pos, const double* true_flow,
+                uint64_t trial_begin, uint64_t trials, uint64_t seed,
+                double* sums_out);
+
+/* overlap (simulation.py:124-136) split so shards can merge: range, then 100-bin counts over
+ * [lo,hi] with numpy's histogram binning (last bin closed). */
+int ofb_minmax(ofb_ctx* ctx, const double* data, size_t n, double* lo_out, double* hi_out);
+int ofb_histogram(ofb_ctx* ctx, const double* data, size_t n, double lo, double hi, int bins,
+                  unsigned long long* counts_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB200_H */

@@ -1,0 +1,115 @@
+"""Pins the C oracle of the image stages (oracle/of_oracle.c) to OpenCV 4.13.0: against the committed
+cv2 outputs (tests/golden/cv2_golden.npz) and, where cv2 is importable, against cv2 run live with the
+reference's literal parameter sets."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import image_oracle as io
+import synth
+
+FEATURE_SETS = {"node": (100, 0.7, 10, 12), "exp": (20, 0.7, 10, 7), "module": (50, 0.3, 20, 32), "bench": (200, 0.01, 10, 7)}
+LK_SETS = {"node": ((15, 15), 3, (3, 20, 0.03)), "module": ((15, 15), 3, (3, 10, 0.5))}
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "cv2_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_pyrdown_bit_exact(g, name):
+    lv = g[name + "_prev"]
+    for l in range(1, 5):
+        lv = io.pyr_down(lv)
+        assert np.array_equal(lv, g["%s_pyr%d" % (name, l)])
+
+
+def test_bgr2gray_bit_exact(g):
+    real = np.load(os.path.join(GOLDEN, "picture_test.npy"))
+    assert np.array_equal(io.bgr2gray(real), g["real_gray"])
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_min_eig_map_close(g, name):
+    img = g[name + "_prev"]
+    for bs in (3, 7, 12):
+        e = io.min_eig_map(img, bs)
+        mx = float(g["%s_eigmax_%d" % (name, bs)])
+        assert abs(e.max() - mx) <= 2e-6 * mx
+        assert np.abs(e[::7, ::5] - g["%s_eigsub_%d" % (name, bs)]).max() <= 2e-6 * mx
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_lk_matches_cv2(g, name):
+    a, b = g[name + "_prev"], g[name + "_next"]
+    pts = g["%s_gftt_bench" % name]
+    for ls, (win, ml, crit) in LK_SETS.items():
+        nxt, st, err = io.pyrlk(a, b, pts, win, ml, crit)
+        gs = g["%s_lk_%s_status" % (name, ls)]
+        assert np.array_equal(st, gs)
+        ok = gs.ravel() == 1
+        assert np.abs(nxt - g["%s_lk_%s_next" % (name, ls)])[ok].max() <= 5e-3
+        assert np.abs(err - g["%s_lk_%s_err" % (name, ls)])[ok].max() <= 5e-3
+
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.mark.parametrize("shape,seed", [((240, 320), 1), ((241, 323), 2), ((480, 640), 3)])
+def test_selection_exact_on_cv2_map(shape, seed):
+    """Feature SELECTION (threshold, NMS, ordering, tie rule, min-distance grid) must equal cv2's
+    exactly when both start from cv2's own lambda_min map."""
+    img = synth.texture(shape[0], shape[1], seed)
+    for mc, q, md, bs in list(FEATURE_SETS.values()) + [(0, 0.05, 0, 3), (300, 0.02, 7.5, 5), (50, 0.01, 1.0, 3)]:
+        ce = cv2.cornerMinEigenVal(img, bs)
+        ours = io.select_features(ce, mc, q, md)
+        ref = cv2.goodFeaturesToTrack(img, mc, q, md, blockSize=bs)
+        if ref is None:
+            assert ours is None
+        else:
+            assert np.array_equal(ours, ref), (mc, q, md, bs)
+
+
+def test_selection_mask_and_ties():
+    img = synth.texture(240, 320, 5)
+    mask = np.ones_like(img)
+    mask[60:140, 100:220] = 0
+    ce = cv2.cornerMinEigenVal(img, 7)
+    assert np.array_equal(io.select_features(ce, 100, 0.01, 10, mask), cv2.goodFeaturesToTrack(img, 100, 0.01, 10, mask=mask, blockSize=7))
+    # exact ties: a periodic pattern repeats the same lambda_min many times
+    yy, xx = np.mgrid[0:128, 0:160]
+    tie = (((xx // 8) + (yy // 8)) % 2 * 200).astype(np.uint8)
+    ce = cv2.cornerMinEigenVal(tie, 3)
+    ref = cv2.goodFeaturesToTrack(tie, 0, 0.5, 5, blockSize=3)
+    assert np.array_equal(io.select_features(ce, 0, 0.5, 5), ref)
+    # all-zero mask / flat image -> None
+    assert io.select_features(ce, 10, 0.5, 5, np.zeros_like(tie)) is None
+    assert io.good_features(np.full((50, 60), 7, np.uint8), 10, 0.01, 5) is None
+
+
+@pytest.mark.parametrize("case", ["shift40", "halfflat", "small_nonsquare", "border"])
+def test_lk_edge_cases_live(case):
+    if case == "shift40":
+        a = synth.texture(240, 320, 7); b = np.roll(a, 40, axis=1)
+        pts = cv2.goodFeaturesToTrack(a, 80, 0.01, 10, blockSize=7); kw = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+    elif case == "halfflat":
+        a = synth.texture(240, 320, 8); a[:, 160:] = 128; b = np.roll(a, 2, axis=0)
+        yy, xx = np.mgrid[20:220:25, 20:300:28]; pts = np.stack([xx.ravel(), yy.ravel()], 1).astype(np.float32).reshape(-1, 1, 2)
+        kw = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+    elif case == "small_nonsquare":
+        a, b = synth.affine_pair(50, 70, 9, shift=(1.2, 0.7), rot=0.0, scale=1.0)
+        pts = cv2.goodFeaturesToTrack(a, 30, 0.01, 5, blockSize=3); kw = dict(winSize=(21, 11), maxLevel=4, criteria=(3, 30, 0.01))
+    else:
+        a, b = synth.affine_pair(120, 160, 10, shift=(-2.5, 3.5))
+        pts = np.array([[0, 0], [1.5, 2.5], [159, 119], [158.2, 3.3], [4, 117.5], [80, 0.4], [0.2, 60]], np.float32).reshape(-1, 1, 2)
+        kw = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 20, 0.03))
+    n2, s2, e2 = cv2.calcOpticalFlowPyrLK(a, b, pts, None, **kw)
+    n1, s1, e1 = io.pyrlk(a, b, pts, kw["winSize"], kw["maxLevel"], kw["criteria"])
+    assert np.array_equal(s1, s2)
+    ok = s2.ravel() == 1
+    if ok.any():
+        assert np.abs(n1 - n2)[ok].max() <= 0.05
+        assert np.abs(e1 - e2)[ok].max() <= 0.05
