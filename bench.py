@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement (BASELINE.json): 1080p frame-pairs/s (detect + LK flow + velocity
+solve) and Monte-Carlo trials/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (pyramids -> Shi-Tomasi -> pyramidal LK -> velocity solve) over one
+batch of `--batch` independent synthetic 1080p frame pairs (BASELINE config 2: 1000 features, maxLevel 4).
+  value      pairs/s with the frames already resident in HBM, CUDA events on the library's stream
+  e2e        the same through the public Python API with pinned HOST frames: H2D of both frames and D2H
+             of the results inside the timed region
+  roofline   the dominant kernel: algorithmic bytes per launch / its CUDA-event duration, vs the measured
+             HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  cv2 4.13 goodFeaturesToTrack + calcOpticalFlowPyrLK (the reference's own un-vendored
+             dependency) + the oracle port of the reference's Python solve_lgs, on the host cores
+  mc         Monte-Carlo error sweep (config 3): 1e8 trials x 50 points, trial ranges sharded over ranks
+With N>1 every rank processes its own batch (streams shard with no data-path collective): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, K_FEAT, MAX_LEVEL = 1920, 1080, 1000, 4
+QUALITY, MIN_DIST, BLOCK = 0.01, 10.0, 7
+WIN, CRIT = (15, 15), (3, 20, 0.03)
+METRIC = "1080p frame-pairs/s (LK flow+velocity solve)"
+MC_TOTAL, MC_POINTS = 100_000_000, 50
+MC_AXES = ("flow_errors", "distance_error", "ang_vel_error", "normal_error", "translation_error", "orientation",
+           "height", "point_position")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs generated (tiled to the batch)")
+    ap.add_argument("--mc-trials", type=int, default=MC_TOTAL)
+    ap.add_argument("--no-mc", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-pairs", type=int, default=4, help="pairs per step of the reference arm")
+    return ap.parse_args()
+
+
+def make_data(distinct, rank):
+    import synth
+    pairs = [synth.make_pair(H, W, stream_id=rank, pair_id=100 * rank + i) for i in range(distinct)]
+    return pairs
+
+
+def imu_array(ofb200, pairs, batch):
+    imu = np.zeros(batch, ofb200._lib.IMU_DTYPE)
+    for i in range(batch):
+        mo = pairs[i % len(pairs)][2]
+        imu["d"][i], imu["n"][i], imu["w"][i] = mo["d"], mo["n"], mo["w"]
+    return imu
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
+    """The reference's CPU path on identical frames: cv2 gftt + LK + Python solve_lgs (oracle port)."""
+    import cv2
+    from oracle import velocity_oracle as vo
+    cv2.setNumThreads(threads)
+    done, t0 = 0, time.perf_counter()
+    split = np.zeros(3)
+    while True:
+        a, b, mo = pairs[done % len(pairs)]
+        t1 = time.perf_counter()
+        p = cv2.goodFeaturesToTrack(a, K_FEAT, QUALITY, MIN_DIST, blockSize=BLOCK)
+        t2 = time.perf_counter()
+        nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=WIN, maxLevel=MAX_LEVEL, criteria=CRIT)
+        t3 = time.perf_counter()
+        ok = st.ravel() == 1
+        newp = nxt.reshape(-1, 2)[ok]
+        x = (newp.astype(np.float64) - np.array([mo["cx"], mo["cy"]])) / mo["f"]
+        u = (newp - p.reshape(-1, 2)[ok]).astype(np.float64) / (mo["f"] * mo["dt"])
+        vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], variant="node")
+        t4 = time.perf_counter()
+        split += [t2 - t1, t3 - t2, t4 - t3]
+        done += 1
+        el = time.perf_counter() - t0
+        if (max_pairs and done >= max_pairs) or (not max_pairs and el >= seconds and done >= 3):
+            break
+    return done / el, done, (split / done * 1e3).tolist()
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = len(os.sched_getaffinity(0))
+    pairs = make_data(min(args.distinct, 4), 0)
+    for _ in range(args.warmup):
+        cpu_pair_path(pairs, 0, ncores, max_pairs=1)
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        _, n, split = cpu_pair_path(pairs, 0, ncores, max_pairs=args.ref_pairs)
+        tot += n
+    el = time.perf_counter() - t0
+    val = tot / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": "C2: 1920x1080 frame pairs, 1000 features, maxLevel 4, detect+track+solve",
+                       "pairs_per_step": args.ref_pairs},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": ncores, "kind": "port",
+                             "sample": "%d pairs: cv2 4.13 goodFeaturesToTrack+calcOpticalFlowPyrLK + oracle port of the "
+                                       "reference's Python solve_lgs, all host threads; ms gftt/LK/solve = %s" %
+                                       (tot, [round(s, 1) for s in split])},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def mc_workload(ofb200, trials_total):
+    sim = ofb200.simulation
+    pts = np.load(os.path.join(ROOT, "tests", "golden", "points.npy"))[:MC_POINTS]
+    steps, pos, flow = [], [], []
+    for name in MC_AXES:
+        s, p, f = sim.build_sweep(name, pts)
+        off = sum(len(q) for q in pos)
+        for st in s:
+            st.pos_offset += off
+        steps += s; pos.append(p); flow.append(f)
+    per_step = -(-trials_total // len(steps))
+    return steps, np.vstack(pos), np.vstack(flow), per_step
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import torch
+    import ofb200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = ofb200.Context(local)
+    B = args.batch
+    pairs = make_data(args.distinct, rank)
+    mo0 = pairs[0][2]
+    cfg = ofb200.make_pair_cfg(W, H, K_FEAT, QUALITY, MIN_DIST, BLOCK, WIN, MAX_LEVEL, CRIT, variant="node",
+                               principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"],
+                               flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
+    imu = imu_array(ofb200, pairs, B)
+    # host frames in pinned memory (e2e path) and a resident copy in HBM (kernel path)
+    h_prev = ctx.pinned_array((B, H, W), np.uint8)
+    h_next = ctx.pinned_array((B, H, W), np.uint8)
+    for i in range(B):
+        h_prev[i], h_next[i] = pairs[i % len(pairs)][0], pairs[i % len(pairs)][1]
+    d_prev = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+    d_next = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
+    ctx.memcpy(d_prev, h_prev, h_prev.nbytes)
+    ctx.memcpy(d_next, h_next, h_next.nbytes)
+    d_imu = torch.from_numpy(imu.view(np.uint8).reshape(-1).copy()).cuda()
+    d_res = torch.zeros(B * ofb200._lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    lib, C = ctx.lib, __import__("ctypes")
+
+    def step_resident():
+        ofb200._lib.check(lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, ofb200._lib.ptr(d_prev), ofb200._lib.ptr(d_next), W,
+                                              W * H, ofb200._lib.ptr(d_imu), None, None, ofb200._lib.ptr(d_res), None, None,
+                                              None))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    l0 = ctx.launch_count()
+    with ClockSampler(local) as clk:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            step_resident()
+        ms = ctx.timer_stop()
+    launches = ctx.launch_count() - l0
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+    # correctness of what was timed: results must be plausible velocities
+    res = np.zeros(B, ofb200._lib.RESULT_DTYPE)
+    ctx.memcpy(res, d_res, res.nbytes)
+    verr = max(np.abs(res["v"][i] - pairs[i % len(pairs)][2]["v"]).max() for i in range(B))
+    tracked = int(res["n_tracked"].min())
+
+    # per-stage durations (CUDA events between the kernels of the same call path)
+    ctx.set_profile(True)
+    for _ in range(args.steps):
+        step_resident()
+    stage_ms, calls = ctx.stage_times()
+    ctx.set_profile(False)
+    stage_ms = [s / max(calls, 1) for s in stage_ms]
+    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_candidates_kernel", "select_kernel",
+             "lk_track_kernel", "pair_solve_kernel"]
+    P = W * H
+    g = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(1, MAX_LEVEL + 1))
+    nfeat = float(res["n_features"].mean())
+    nlev = MAX_LEVEL + 1
+    alg = [2 * (P + g) * B,
+           (P + 8 * 4 * nfeat) * B,
+           (8 * 4 * nfeat + 8 * nfeat) * B,
+           (21 * nfeat + nfeat * nlev * ((WIN[0] + 3) * (WIN[1] + 3) + (WIN[0] + 1) * (WIN[1] + 1))) * B,
+           (17 * nfeat + 80) * B]
+    dom = int(np.argmax(stage_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "stage_ms": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s, 4) for s in stage_ms])),
+                "stage_gbs": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"],
+                                      [round(a / (s * 1e-3) / 1e9, 2) if s > 0 else None for a, s in zip(alg, stage_ms)])),
+                "note": "LK is latency/issue bound (dependent Newton iterations), not HBM bound; see DESIGN.md"}
+
+    # end to end through the public API: pinned host frames in, host results out, every step
+    for _ in range(max(1, args.warmup // 2)):
+        ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * P + imu.nbytes),
+           "d2h_bytes_per_step": int(r.nbytes)}
+
+    # Monte-Carlo sweep, trial ranges sharded over the ranks, sums merged with one all-reduce
+    mc = None
+    if not args.no_mc:
+        sim = ofb200.simulation
+        steps, pos, flow, per_step = mc_workload(ofb200, args.mc_trials)
+        begin, count = sim.shard_range(per_step, rank, world)
+        sim.run_steps(steps, pos, flow, max(count // 10, 1), seed=1, trial_begin=begin, ctx=ctx)      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        sums = sim.run_steps(steps, pos, flow, count, seed=1, trial_begin=begin, ctx=ctx)
+        mc_ms = ctx.timer_stop()
+        if dist is not None:
+            sums = sim.merge_sums(sums, None, torch.device("cuda", local))
+            t = torch.tensor([mc_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mc_ms = float(t.item())
+        mc_wall = time.perf_counter() - t0
+        mean, std, mR, n = sim.stats_from_sums(sums, steps)
+        total = float(n.sum())
+        flop = 140 * MC_POINTS + 300
+        mc = {"metric": "MC trials/s", "value": total / (mc_ms * 1e-3), "unit": "trials/s", "trials": total,
+              "points": MC_POINTS, "steps": len(steps), "axes": list(MC_AXES), "ms": mc_ms, "wall_ms": mc_wall * 1e3,
+              "scaling": "strong", "precision": "fp32 per-point, fp64 solve/statistics",
+              "fp32_tflops_alg": total * flop / (mc_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
+              "check_mean_v_step0": [round(float(x), 4) for x in mean[0]]}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        ncores = len(os.sched_getaffinity(0))
+        try:
+            v, n, split = cpu_pair_path(pairs, 12.0, ncores)
+            cpu = {"value": v, "unit": "pairs/s", "cores": ncores, "kind": "port",
+                   "sample": "%d pairs of the same workload: cv2 4.13 gftt+pyrLK + oracle port of the reference's Python "
+                             "solve_lgs, %d threads; ms gftt/LK/solve = %s" % (n, ncores, [round(s, 1) for s in split])}
+        except Exception as e:   # cv2 missing on the box
+            cpu = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "port", "sample": "unavailable: %r" % (e,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+                "config": {"workload": "C2: 1920x1080 frame pairs, 1000 features, maxLevel 4, detect+track+solve",
+                           "pairs_per_step_per_gpu": B, "distinct_pairs": len(pairs),
+                           "l2": "inputs larger than L2 (%d MB of frames per step)" % (2 * B * P // 2 ** 20),
+                           "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk.summary(), "mc": mc,
+                "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "ofb_ctx_sync": (i32, [vp]),
     "ofb_ctx_stream": (i32, [vp, C.POINTER(vp)]),
     "ofb_ctx_launch_count": (i32, [vp, C.POINTER(u64)]),
+    "ofb_ctx_set_profile": (i32, [vp, i32]),
+    "ofb_ctx_stage_times": (i32, [vp, C.POINTER(C.c_float), C.POINTER(u64)]),
     "ofb_timer_start": (i32, [vp]),
     "ofb_timer_stop": (i32, [vp, C.POINTER(C.c_float)]),
     "ofb_dev_alloc": (i32, [vp, sz, C.POINTER(vp)]),
@@ -176,6 +178,16 @@ class Context:
         n = u64()
         check(self.lib.ofb_ctx_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def set_profile(self, enable=True):
+        check(self.lib.ofb_ctx_set_profile(self.h, 1 if enable else 0))
+
+    def stage_times(self):
+        """(ms[5] accumulated over calls: pyramids, lambda_min+NMS, selection, LK, solve; n_calls)"""
+        ms = (C.c_float * 5)()
+        n = u64()
+        check(self.lib.ofb_ctx_stage_times(self.h, ms, C.byref(n)))
+        return [float(x) for x in ms], n.value
 
     def timer_start(self):
         check(self.lib.ofb_timer_start(self.h))

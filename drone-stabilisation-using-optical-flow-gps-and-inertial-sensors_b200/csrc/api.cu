@@ -60,6 +60,7 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
     for (int i = 0; i < 2; ++i) if (ctx->pair_pyr[i]) { cudaFree(ctx->pair_pyr[i]->base); delete ctx->pair_pyr[i]; }
     for (int i = 0; i < OFB_NSCRATCH; ++i) ctx->scratch[i].release();
     for (int i = 0; i < 4; ++i) ctx->pin[i].release();
+    for (int i = 0; i < OFB_NSTAGE_EV; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -141,5 +142,24 @@ extern "C" int ofb_memcpy(ofb_ctx* ctx, void* dst, const void* src, size_t bytes
 {
     OFB_TRY(ofb_memcpy_async(ctx, dst, src, bytes));
     OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OFB_OK;
+}
+
+extern "C" int ofb_ctx_set_profile(ofb_ctx* ctx, int enable)
+{
+    OFB_REQUIRE(ctx, "ctx_set_profile: null context");
+    if (enable && !ctx->stage_ev[0])
+        for (int i = 0; i < OFB_NSTAGE_EV; ++i) OFB_CUDA(cudaEventCreate(&ctx->stage_ev[i]));
+    ctx->profile = enable != 0;
+    for (int i = 0; i < OFB_NSTAGES; ++i) ctx->stage_ms[i] = 0.f;
+    ctx->stage_calls = 0;
+    return OFB_OK;
+}
+
+extern "C" int ofb_ctx_stage_times(ofb_ctx* ctx, float* ms_out, uint64_t* calls_out)
+{
+    OFB_REQUIRE(ctx && ms_out, "ctx_stage_times: null argument");
+    for (int i = 0; i < OFB_NSTAGES; ++i) ms_out[i] = ctx->stage_ms[i];
+    if (calls_out) *calls_out = ctx->stage_calls;
     return OFB_OK;
 }

@@ -70,7 +70,7 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { OFB_NSCRATCH = 24 };
+enum { OFB_NSCRATCH = 24, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6 };
 
 struct ofb_ctx {
     int device = 0;
@@ -83,6 +83,11 @@ struct ofb_ctx {
     PinBuf pin[4];
     std::vector<ofb_pyr*> pyramids;
     ofb_pyr* pair_pyr[2] = {nullptr, nullptr};   // workspace pyramids of ofb_frame_pairs
+    // optional per-stage CUDA-event timing of ofb_frame_pairs (ofb_ctx_set_profile)
+    bool profile = false;
+    cudaEvent_t stage_ev[OFB_NSTAGE_EV] = {};
+    float stage_ms[OFB_NSTAGES] = {};
+    uint64_t stage_calls = 0;
 };
 
 // scratch roles

@@ -62,7 +62,9 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     OFB_REQUIRE(cfg->detect || (pts_in && n_in), "frame_pairs: detect==0 needs pts_in and n_in");
     OFB_REQUIRE(n_pairs == 1 || image_stride >= (size_t)pitch * (h - 1) + w, "frame_pairs: image_stride too small");
     OFB_CUDA(cudaSetDevice(ctx->device));
+#define STAGE_MARK(i) do { if (ctx->profile) OFB_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream)); } while (0)
     // stage 1: both pyramids (levels >= 1); host frames are copied into the workspace level 0
+    STAGE_MARK(0);
     OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0], prev, w, h, pitch, image_stride, n_pairs, cfg->max_level));
     OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[1], next, w, h, pitch, image_stride, n_pairs, cfg->max_level));
     ofb_pyr* pp = ctx->pair_pyr[0];
@@ -78,6 +80,7 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     if (!d_prev) { OFB_TRY(ctx->scratch[SC_PTS0].reserve(sizeof(float) * 2 * npts)); d_prev = ctx->scratch[SC_PTS0].as<float>(); }
     if (!d_next) { OFB_TRY(ctx->scratch[SC_PTS1].reserve(sizeof(float) * 2 * npts)); d_next = ctx->scratch[SC_PTS1].as<float>(); }
     if (!d_stat) { OFB_TRY(ctx->scratch[SC_STAT].reserve(npts)); d_stat = ctx->scratch[SC_STAT].as<uint8_t>(); }
+    STAGE_MARK(1);
     const void* dimu;
     OFB_TRY(ofb_stage_in(ctx, SC_IN3, imu, sizeof(ofb_imu_sample) * n_pairs, &dimu));
     const int* counts; int counts_stride;
@@ -102,14 +105,33 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
         counts = (const int*)dn; counts_stride = 1;
     }
     // stage 3
+    STAGE_MARK(3);
     OFB_TRY(ctx->scratch[SC_ERR].reserve(sizeof(float) * npts));
     OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, 0, 1, n_pairs, d_prev, counts, counts_stride, K, (size_t)K, cfg->win_w,
                           cfg->win_h, cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, d_next, d_stat,
                           ctx->scratch[SC_ERR].as<float>()));
     // stage 4
+    STAGE_MARK(4);
     TrackLoader ld{d_prev, d_next, d_stat, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
     pair_solve_kernel<<<n_pairs, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, (const ofb_imu_sample*)dimu,
                                                                      (ofb_pair_result*)o[3].dev);
     OFB_LAUNCH_CHECK(ctx);
-    return ofb_finish_out(ctx, o, 4);
+    STAGE_MARK(5);
+    int rc = ofb_finish_out(ctx, o, 4);
+    if (rc == OFB_OK && ctx->profile) {
+        // stage order: 0 pyramids (+H2D of host frames), 1 lambda_min+NMS, 2 ordered selection, 3 LK, 4 solve
+        OFB_CUDA(cudaEventSynchronize(ctx->stage_ev[5]));
+        for (int i = 0; i < OFB_NSTAGES; ++i) {
+            float ms = 0.f;
+            if (cfg->detect || (i != 1 && i != 2)) {
+                int e0 = i, e1 = i + 1;
+                if (!cfg->detect && i == 0) e1 = 1;
+                if (!cfg->detect && i == 3) e0 = 3;
+                OFB_CUDA(cudaEventElapsedTime(&ms, ctx->stage_ev[e0], ctx->stage_ev[e1]));
+            }
+            ctx->stage_ms[i] += ms;
+        }
+        ctx->stage_calls++;
+    }
+    return rc;
 }

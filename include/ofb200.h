@@ -52,6 +52,11 @@ int ofb_ctx_sync(ofb_ctx* ctx);
 int ofb_ctx_stream(ofb_ctx* ctx, void** cuda_stream_out);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int ofb_ctx_launch_count(ofb_ctx* ctx, uint64_t* out);
+/* per-stage CUDA-event timing of ofb_frame_pairs on the context's stream. ms_out[5] accumulates, in
+ * order: pyramids (+H2D of host frames), lambda_min+NMS kernel, ordered-selection kernel, LK kernel,
+ * velocity-solve kernel; *calls_out = number of ofb_frame_pairs calls accumulated. */
+int ofb_ctx_set_profile(ofb_ctx* ctx, int enable);
+int ofb_ctx_stage_times(ofb_ctx* ctx, float* ms_out, uint64_t* calls_out);
 /* CUDA-event bracket on the context's stream: ofb_timer_start, ..., ofb_timer_stop -> ms */
 int ofb_timer_start(ofb_ctx* ctx);
 int ofb_timer_stop(ofb_ctx* ctx, float* ms_out);

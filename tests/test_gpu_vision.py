@@ -1,0 +1,210 @@
+"""GPU parity, stages 0-3 (through the C ABI) against the C oracle, the committed cv2 4.13 outputs and
+cv2 live (the GPU box runs the same image). Bars: pyramid bit-exact; feature lists equal
+as ordered lists except documented float ties; LK <= 0.05 px with identical status."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import image_oracle as io
+import synth
+
+pytestmark = pytest.mark.gpu
+
+FEATURE_SETS = {"node": (100, 0.7, 10, 12), "exp": (20, 0.7, 10, 7), "module": (50, 0.3, 20, 32), "bench": (200, 0.01, 10, 7)}
+LK_SETS = {"node": ((15, 15), 3, (3, 20, 0.03)), "module": ((15, 15), 3, (3, 10, 0.5))}
+TIE_TOL = 2.0 ** -20       # documented tie: |d lambda_min| <= 2^-20 * max lambda_min
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "cv2_golden.npz"))
+
+
+def as_list(p):
+    return np.zeros((0, 2), np.float32) if p is None else np.asarray(p).reshape(-1, 2)
+
+
+def check_features(ofb200, ctx, img, mc, q, md, bs, mask=None, ref=None):
+    """The contract: the GPU list is OpenCV's selection rule applied EXACTLY to a lambda_min map that is
+    within the tie tolerance of OpenCV's map. Returns True when it is also identical to cv2's list."""
+    got = as_list(ofb200.goodFeaturesToTrack(img, mc, q, md, mask=mask, blockSize=bs, ctx=ctx))
+    eig = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
+    expect = as_list(io.select_features(eig, mc, q, md, mask))
+    assert np.array_equal(got, expect), "selection differs from OpenCV's rule on the GPU's own map"
+    oeig = io.min_eig_map(img, bs)
+    assert np.abs(eig - oeig).max() <= 4 * TIE_TOL * max(float(oeig.max()), 1e-30), "lambda_min map outside tie tolerance"
+    if ref is not None:
+        ref = as_list(ref)
+        return got.shape == ref.shape and np.array_equal(got, ref)
+    return True
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_pyramid_bit_exact_vs_cv2_golden(ctx, g, name):
+    import ofb200
+    lv = ofb200.buildPyramid(g[name + "_prev"], 4, ctx=ctx)
+    assert len(lv) == 5
+    for l in range(1, 5):
+        assert np.array_equal(lv[l], g["%s_pyr%d" % (name, l)]), (name, l)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (5, 4), (17, 33), (63, 129), (64, 128), (65, 131), (240, 320), (1080, 1920)])
+def test_pyramid_shapes_vs_oracle(ctx, shape):
+    import ofb200
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    lv = ofb200.buildPyramid(img, 6, ctx=ctx)
+    ref = io.build_pyramid(img, len(lv) - 1)
+    for a, b in zip(lv, ref):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_pyramid_batch_and_checksum_at_full_size(ctx):
+    """Batch of 1080p frames: every image's levels equal the single-image result (size-independent
+    property) and level 1 of a constant image stays constant."""
+    import ofb200
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (3, 1080, 1920), dtype=np.uint8)
+    imgs[2] = 137
+    p = ofb200.Pyramid(imgs, 4, ctx=ctx)
+    for i in range(3):
+        single = ofb200.buildPyramid(imgs[i], 4, ctx=ctx)
+        for l in range(5):
+            assert np.array_equal(p.level(l, i), single[l])
+    assert np.all(p.level(4, 2) == 137)
+    assert np.array_equal(p.level(1, 0), io.pyr_down(imgs[0]))
+    p.close()
+
+
+def test_bgr2gray(ctx, g):
+    import ofb200
+    real = np.load(os.path.join(GOLDEN, "picture_test.npy"))
+    assert np.array_equal(ofb200.cvtColor(real, ofb200.COLOR_BGR2GRAY, ctx=ctx), g["real_gray"])
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    assert np.array_equal(ofb200.cvtColor(bgr, ctx=ctx), io.bgr2gray(bgr))
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_features_vs_cv2_golden(ctx, g, name):
+    import ofb200
+    img = g[name + "_prev"]
+    identical = 0
+    for fs, (mc, q, md, bs) in FEATURE_SETS.items():
+        identical += check_features(ofb200, ctx, img, mc, q, md, bs, ref=g["%s_gftt_%s" % (name, fs)])
+    assert identical >= 3, "more than one parameter set needed the tie rule on %s" % name
+
+
+def test_features_masked_and_edge_cases(ctx, g):
+    import ofb200
+    img = g["c1_prev"]
+    assert check_features(ofb200, ctx, img, 80, 0.01, 10, 7, mask=g["c1_mask"], ref=g["c1_gftt_masked"])
+    # unlimited corners, no min distance; non-integer distance; distance 1
+    for mc, q, md, bs in [(0, 0.05, 0, 3), (300, 0.02, 7.5, 5), (50, 0.01, 1.0, 3), (5000, 0.001, 3, 3), (0, 0.2, 12, 7)]:
+        check_features(ofb200, ctx, img, mc, q, md, bs)
+    # flat image and all-zero mask -> None, as cv2
+    assert ofb200.goodFeaturesToTrack(np.full((50, 60), 7, np.uint8), 10, 0.01, 5, ctx=ctx) is None
+    assert ofb200.goodFeaturesToTrack(img, 10, 0.01, 5, mask=np.zeros_like(img), ctx=ctx) is None
+    # exact ties (periodic pattern): ordering rule "larger address first"
+    yy, xx = np.mgrid[0:128, 0:160]
+    tie = (((xx // 8) + (yy // 8)) % 2 * 200).astype(np.uint8)
+    check_features(ofb200, ctx, tie, 0, 0.5, 5, 3)
+    check_features(ofb200, ctx, tie, 40, 0.5, 0, 3)
+    with pytest.raises(ValueError):
+        ofb200.goodFeaturesToTrack(img.astype(np.float32), 10, 0.01, 5, ctx=ctx)
+    with pytest.raises(ValueError):
+        ofb200.goodFeaturesToTrack(img, 10, 0.01, 5, blockSize=99, ctx=ctx)
+
+
+def test_features_live_cv2_many_sizes(ctx):
+    import ofb200
+    cv2 = pytest.importorskip("cv2")
+    same = total = 0
+    for (h, w), seed in [((240, 320), 1), ((241, 323), 2), ((480, 640), 3), ((720, 1280), 4), ((1080, 1920), 5)]:
+        img = synth.texture(h, w, seed)
+        for mc, q, md, bs in [(200, 0.01, 10, 7), (1000, 0.01, 10, 7), (100, 0.7, 10, 12), (50, 0.3, 20, 32)]:
+            ref = cv2.goodFeaturesToTrack(img, mc, q, md, blockSize=bs)
+            same += check_features(ofb200, ctx, img, mc, q, md, bs, ref=ref)
+            total += 1
+    assert same >= total - 3, (same, total)
+
+
+@pytest.mark.parametrize("name", ["real", "c1", "odd"])
+def test_lk_vs_cv2_golden(ctx, g, name):
+    import ofb200
+    a, b = g[name + "_prev"], g[name + "_next"]
+    pts = g["%s_gftt_bench" % name]
+    for ls, (win, ml, crit) in LK_SETS.items():
+        nxt, st, err = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, winSize=win, maxLevel=ml, criteria=crit, ctx=ctx)
+        gs = g["%s_lk_%s_status" % (name, ls)]
+        assert nxt.shape == pts.shape and st.shape == gs.shape and st.dtype == np.uint8 and nxt.dtype == np.float32
+        assert np.array_equal(st, gs), (name, ls, int((st != gs).sum()))
+        ok = gs.ravel() == 1
+        dpos = np.abs(nxt - g["%s_lk_%s_next" % (name, ls)])[ok].max()
+        assert dpos <= 0.05, dpos
+        assert np.abs(err - g["%s_lk_%s_err" % (name, ls)])[ok].max() <= 0.05
+        # and the tighter, informative bound against the scalar oracle (same arithmetic, exact sums)
+        on, os_, oe = io.pyrlk(a, b, pts, win, ml, crit)
+        assert np.array_equal(st, os_)
+        assert np.abs(nxt - on)[ok].max() <= 5e-3
+
+
+@pytest.mark.parametrize("case", ["shift40", "halfflat", "small_nonsquare", "border", "win21", "initial_flow"])
+def test_lk_edge_cases(ctx, case):
+    import ofb200
+    flags = 0
+    init = None
+    if case == "shift40":
+        a = synth.texture(240, 320, 7); b = np.roll(a, 40, axis=1)
+        pts = io.good_features(a, 80, 0.01, 10, block_size=7); kw = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+    elif case == "halfflat":
+        a = synth.texture(240, 320, 8); a[:, 160:] = 128; b = np.roll(a, 2, axis=0)
+        yy, xx = np.mgrid[20:220:25, 20:300:28]; pts = np.stack([xx.ravel(), yy.ravel()], 1).astype(np.float32).reshape(-1, 1, 2)
+        kw = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+    elif case == "small_nonsquare":
+        a, b = synth.affine_pair(50, 70, 9, shift=(1.2, 0.7), rot=0.0, scale=1.0)
+        pts = io.good_features(a, 30, 0.01, 5, block_size=3); kw = dict(winSize=(21, 11), maxLevel=4, criteria=(3, 30, 0.01))
+    elif case == "border":
+        a, b = synth.affine_pair(120, 160, 10, shift=(-2.5, 3.5))
+        pts = np.array([[0, 0], [1.5, 2.5], [159, 119], [158.2, 3.3], [4, 117.5], [80, 0.4], [0.2, 60], [-3, 50], [170, 60]],
+                       np.float32).reshape(-1, 1, 2)
+        kw = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 20, 0.03))
+    elif case == "win21":
+        a, b = synth.affine_pair(240, 320, 11, shift=(4.2, -3.1))
+        pts = io.good_features(a, 60, 0.01, 10, block_size=7); kw = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    else:
+        a, b = synth.affine_pair(240, 320, 12, shift=(6.0, 5.0))
+        pts = io.good_features(a, 40, 0.01, 10, block_size=7); kw = dict(winSize=(15, 15), maxLevel=0, criteria=(3, 20, 0.03))
+        flags = 4
+        init = pts + np.float32([5.5, 4.5])
+    if case == "initial_flow":
+        cv2 = pytest.importorskip("cv2")
+        rn, rs, re_ = cv2.calcOpticalFlowPyrLK(a, b, pts, init.copy(), flags=flags, **kw)
+    else:
+        rn, rs, re_ = io.pyrlk(a, b, pts, kw["winSize"], kw["maxLevel"], kw["criteria"])
+    n, s, e = ofb200.calcOpticalFlowPyrLK(a, b, pts, None if init is None else init.copy(), flags=flags, ctx=ctx, **kw)
+    assert np.array_equal(s, rs), (case, s.ravel(), rs.ravel())
+    ok = rs.ravel() == 1
+    if ok.any():
+        assert np.abs(n - rn)[ok].max() <= 0.05
+        assert np.abs(e - re_)[ok].max() <= 0.05
+    # empty point set
+    n0, s0, e0 = ofb200.calcOpticalFlowPyrLK(a, b, np.zeros((0, 1, 2), np.float32), None, ctx=ctx, **kw)
+    assert n0.shape == (0, 1, 2) and s0.shape == (0, 1)
+
+
+def test_lk_live_cv2_1080p(ctx):
+    """BASELINE config 2 geometry: 1080p, 1000 features, maxLevel 4, against cv2 itself."""
+    import ofb200
+    cv2 = pytest.importorskip("cv2")
+    a, b, mo = synth.make_pair(1080, 1920, 0, 0)
+    pts = cv2.goodFeaturesToTrack(a, 1000, 0.01, 10, blockSize=7)
+    rn, rs, re_ = cv2.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(15, 15), maxLevel=4, criteria=(3, 20, 0.03))
+    n, s, e = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(15, 15), maxLevel=4, criteria=(3, 20, 0.03), ctx=ctx)
+    assert np.array_equal(s, rs)
+    ok = rs.ravel() == 1
+    assert ok.sum() >= 900
+    assert np.abs(n - rn)[ok].max() <= 0.05
+    assert np.median(np.abs(n - rn)[ok]) <= 1e-3
