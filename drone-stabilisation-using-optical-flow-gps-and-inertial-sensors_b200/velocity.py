@@ -108,10 +108,11 @@ def feasibility(position, linear_velocity, flow, angular_velocity, translation, 
     x = _pts(position, "position")
     u = _pts(flow, "flow")
     out = np.zeros((2, len(x)))
-    _lib.check(ctx.lib.ofb_feasibility(ctx.h, _lib.ptr(x), _lib.ptr(_vec3(linear_velocity, "linear_velocity")),
-                                       _lib.ptr(u), len(x), _lib.ptr(_vec3(angular_velocity, "angular_velocity")),
-                                       _lib.ptr(_vec3(translation, "translation")), _lib.ptr(_vec3(normal, "normal")),
-                                       _lib.ptr(out)))
+    # keep the converted vectors alive across the call (ptr() does not hold a reference)
+    v3, w3 = _vec3(linear_velocity, "linear_velocity"), _vec3(angular_velocity, "angular_velocity")
+    t3, n3 = _vec3(translation, "translation"), _vec3(normal, "normal")
+    _lib.check(ctx.lib.ofb_feasibility(ctx.h, _lib.ptr(x), _lib.ptr(v3), _lib.ptr(u), len(x), _lib.ptr(w3), _lib.ptr(t3),
+                                       _lib.ptr(n3), _lib.ptr(out)))
     return out
 
 
