@@ -6,20 +6,21 @@
 // separable [1 4 6 4 1]/16 in both axes, decimate by two, reflect-101 borders, integer
 // (sum + 128) >> 8 -- bit-exact with OpenCV.
 //
-// One CTA produces a 64x16 tile of the destination level for one image of the batch (blockIdx.z).
-// The (2*64+4)x(2*16+3) source footprint is staged once in shared memory with 32-bit coalesced loads
-// (byte loads with reflect-101 index fix-up on border tiles only); every thread then produces four
-// horizontally adjacent outputs from 15 LDS.32 and writes them with one 32-bit store. Source bytes are
-// read from HBM exactly once per level (plus the 4-byte halo), so the kernel is HBM-bound:
+// One CTA produces a 64x32 tile of the destination level for one image of the batch (blockIdx.z).
+// The 160x67-byte source footprint is staged once in shared memory with 128-bit coalesced loads
+// (byte loads with reflect-101 index fix-up on border tiles only). Every thread then produces a 4x2
+// block of outputs: the horizontal 5-tap filter of four adjacent outputs is eight dp4a on re-aligned
+// words (funnel shifts) per source row, seven source rows feed both output rows, and each output row is
+// written with one 32-bit store. Source bytes are read from HBM exactly once per level (plus halo):
 // algorithmic bytes per level = w*h read + ((w+1)/2)*((h+1)/2) written.
 #include "common.cuh"
 
 namespace {
 
-constexpr int PT_W = 64, PT_H = 16;                 // output tile
-constexpr int PS_W = 2 * PT_W + 8;                  // staged source columns (word aligned, 4 left + 4 right halo)
-constexpr int PS_H = 2 * PT_H + 3;                  // staged source rows
-constexpr int PS_PITCH = PS_W;                      // bytes, multiple of 4
+constexpr int PT_W = 64, PT_H = 32;                 // output tile
+constexpr int PS_W = 2 * PT_W + 32;                 // staged source columns: 2*X0-16 .. 2*X0+143 (10 x 16 bytes)
+constexpr int PS_H = 2 * PT_H + 3;                  // staged source rows:    2*Y0-2 .. 2*Y0+64
+constexpr int PS_PITCH = PS_W;                      // bytes, multiple of 16
 
 __device__ __forceinline__ int refl101(int p, int len)
 {
@@ -35,17 +36,17 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, siz
     __shared__ __align__(16) uint8_t tile[PS_H * PS_PITCH];
     const uint8_t* s = src + (size_t)blockIdx.z * sstride;
     uint8_t* d = dst + (size_t)blockIdx.z * dstride;
-    int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
-    int sx0 = 2 * X0 - 4, sy0 = 2 * Y0 - 2;         // source coordinate of tile[0][0]
-    bool interior = sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh &&
-                    ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
+    const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
+    const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;   // source coordinate of tile[0][0]
+    const bool interior = sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh &&
+                          ((spitch & 15) == 0) && ((((size_t)s) & 15) == 0);
     if (interior) {
-        const uint32_t* s32 = (const uint32_t*)(s + (size_t)sy0 * spitch + sx0);
-        int wpitch = spitch >> 2;
-        uint32_t* t32 = (uint32_t*)tile;
-        for (int i = threadIdx.x; i < PS_H * (PS_W / 4); i += 256) {
-            int r = i / (PS_W / 4), c = i - r * (PS_W / 4);
-            t32[r * (PS_PITCH / 4) + c] = __ldg(s32 + (size_t)r * wpitch + c);
+        const uint4* s128 = (const uint4*)(s + (size_t)sy0 * spitch + sx0);
+        const int qpitch = spitch >> 4;
+        uint4* t128 = (uint4*)tile;
+        for (int i = threadIdx.x; i < PS_H * (PS_W / 16); i += 256) {
+            int r = i / (PS_W / 16), c = i - r * (PS_W / 16);
+            t128[r * (PS_PITCH / 16) + c] = __ldg(s128 + (size_t)r * qpitch + c);
         }
     } else {
         for (int i = threadIdx.x; i < PS_H * PS_W; i += 256) {
@@ -55,36 +56,39 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, siz
         }
     }
     __syncthreads();
-    int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 outputs each
-    int ox = X0 + 4 * tx, oy = Y0 + ty;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x2 outputs each
+    const int ox = X0 + 4 * tx, oy = Y0 + 2 * ty;
     if (ox >= dw || oy >= dh) return;
-    // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8  -> tile columns 8tx+2 .. 8tx+12
-    // read tile columns 8tx .. 8tx+15 (4 words) for rows 2ty .. 2ty+4
-    int col[16];
+    // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
+    // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
+    // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
+    const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
+    unsigned int hsum[7][4];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) col[c] = 0;
-    const uint32_t* t32 = (const uint32_t*)tile;
-    const int kv[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        const uint32_t* row = t32 + (2 * ty + r) * (PS_PITCH / 4) + 2 * tx;
-        uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-        uint32_t ws[4] = {w0, w1, w2, w3};
-#pragma unroll
-        for (int c = 0; c < 16; ++c) col[c] += kv[r] * (int)((ws[c >> 2] >> (8 * (c & 3))) & 0xffu);
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t* row = t32 + r * (PS_PITCH / 4);
+        unsigned int w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+        unsigned int f01 = __funnelshift_r(w0, w1, 16), f12 = __funnelshift_r(w1, w2, 16), f23 = __funnelshift_r(w2, w3, 16);
+        hsum[r][0] = __dp4a(f12, 0x00000001u, __dp4a(f01, 0x04060401u, 0u));
+        hsum[r][1] = __dp4a(w2, 0x00000001u, __dp4a(w1, 0x04060401u, 0u));
+        hsum[r][2] = __dp4a(f23, 0x00000001u, __dp4a(f12, 0x04060401u, 0u));
+        hsum[r][3] = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x04060401u, 0u));
     }
-    uint32_t packed = 0;
+    const bool vec_ok = ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int b = 2 * k + 2;   // tile-local column of source 2(ox+k)-2
-        int v = col[b] + 4 * col[b + 1] + 6 * col[b + 2] + 4 * col[b + 3] + col[b + 4];
-        packed |= (uint32_t)((v + 128) >> 8) << (8 * k);
-    }
-    uint8_t* drow = d + (size_t)oy * dpitch + ox;
-    if (ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0)) {
-        *(uint32_t*)drow = packed;
-    } else {
-        for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
+    for (int rr = 0; rr < 2; ++rr) {
+        if (oy + rr >= dh) break;
+        unsigned int packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned int v = hsum[2 * rr][k] + hsum[2 * rr + 4][k] + 4u * (hsum[2 * rr + 1][k] + hsum[2 * rr + 3][k]) +
+                             6u * hsum[2 * rr + 2][k];
+            packed |= ((v + 128u) >> 8) << (8 * k);
+        }
+        uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
+        if (vec_ok) *(uint32_t*)drow = packed;
+        else
+            for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
     }
 }
 

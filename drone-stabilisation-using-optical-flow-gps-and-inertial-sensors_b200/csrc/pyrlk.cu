@@ -221,6 +221,245 @@ lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restric
     }
 }
 
+// ================= register-resident fast path: winW <= 16, winH <= 15 (the reference uses 15x15) ============
+// lane = (row r = lane>>1, half hh = lane&1): the lane owns the 8 window pixels (8hh+k, r), k=0..7, for the
+// whole track. Everything a lane needs sits in 12-byte row segments (three 32-bit words after re-alignment with
+// funnel shifts): no shared memory, no byte-granular traffic. Row r+1 of the window comes from lane+2 by
+// shuffle (the two lanes of row 15 only feed their neighbours). The Q14 bilinear taps of the image are two
+// dp2a (16-bit weights x u8 pixels) per pixel; a funnel shift yields the byte pairs of pixels k and k+2 at once.
+constexpr int LKF_WARPS = 4;
+
+__device__ __forceinline__ int dp2a_lo(int w16x2, unsigned int bytes, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(int w16x2, unsigned int bytes, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(c));
+    return d;
+}
+
+// 12 bytes of row Y starting at column X0 (bytes j=0..11 <-> columns X0+j) as three words.
+// fast: the 16 bytes from the aligned-down address are inside the row; slow: per-byte reflect-101.
+__device__ __forceinline__ void load12(const uint8_t* __restrict__ img, int w, int h, int pitch, int X0, int Y, bool fast,
+                                       unsigned int& o0, unsigned int& o1, unsigned int& o2)
+{
+    if (fast) {
+        const uint8_t* p = img + (size_t)Y * pitch + X0;
+        unsigned long long a = (unsigned long long)p;
+        const unsigned int* q = (const unsigned int*)(a & ~3ull);
+        unsigned int sh = (unsigned int)(a & 3ull) * 8u;
+        unsigned int a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+        o0 = __funnelshift_r(a0, a1, sh); o1 = __funnelshift_r(a1, a2, sh); o2 = __funnelshift_r(a2, a3, sh);
+    } else {
+        const uint8_t* row = img + (size_t)refl101(Y, h) * pitch;
+        unsigned int v[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[j >> 2] |= (unsigned int)__ldg(row + refl101(X0 + j, w)) << (8 * (j & 3));
+        o0 = v[0]; o1 = v[1]; o2 = v[2];
+    }
+}
+
+__device__ __forceinline__ int byte_of(unsigned int w0, unsigned int w1, unsigned int w2, int j)
+{   // j is a compile-time constant after unrolling
+    unsigned int w = j < 4 ? w0 : (j < 8 ? w1 : w2);
+    return (int)((w >> (8 * (j & 3))) & 0xffu);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the lane's 8 pixels of f(jv_k) where jv_k is the Q5 interpolated value of J at pixel k
+#define LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, BODY)                                     \
+    {                                                                                             \
+        unsigned int t1_ = __funnelshift_r(T0, T1, 8), t5_ = __funnelshift_r(T1, T2, 8);          \
+        unsigned int u1_ = __funnelshift_r(U0, U1, 8), u5_ = __funnelshift_r(U1, U2, 8);          \
+        unsigned int tt_[4] = {T0, t1_, T1, t5_};                                                 \
+        unsigned int uu_[4] = {U0, u1_, U1, u5_};                                                 \
+        _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                           \
+            int s_ = ((k >> 2) << 1) | (k & 1);       /* k=0,1,2,3,4,5,6,7 -> 0,1,0,1,2,3,2,3 */  \
+            int jv;                                                                               \
+            if ((k & 2) == 0) { jv = dp2a_lo(Wt, tt_[s_], 256); jv = dp2a_lo(Wb, uu_[s_], jv); }  \
+            else { jv = dp2a_hi(Wt, tt_[s_], 256); jv = dp2a_hi(Wb, uu_[s_], jv); }               \
+            jv >>= 9;                                                                             \
+            BODY                                                                                  \
+        }                                                                                         \
+    }
+
+__global__ void __launch_bounds__(LKF_WARPS * 32)
+lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                     uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
+                     int counts_stride, int n_uniform, size_t pts_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.y;
+    const int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
+    const int feat = blockIdx.x * LKF_WARPS + (threadIdx.x >> 5);
+    if (feat >= n) return;
+    const int winW = P.win_w, winH = P.win_h;
+    const int r = lane >> 1, hh = lane & 1;
+    const size_t po = (size_t)pair * pts_stride + feat;
+    const float ptx = prev_pts[2 * po], pty = prev_pts[2 * po + 1];
+    float nx = 0.f, ny = 0.f;
+    if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = next_pts[2 * po]; ny = next_pts[2 * po + 1]; }
+    const float hwx = (winW - 1) * 0.5f, hwy = (winH - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    // validity of the lane's pixels: column 8hh+k < winW, row r < winH
+    unsigned int vmask = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (8 * hh + k < winW && r < winH) vmask |= 1u << k;
+    bool st = true;
+    float errv = 0.f;
+    const int pimg = P.prev_image0 + pair * P.prev_image_step, nimg = P.next_image0 + pair * P.next_image_step;
+
+    for (int level = P.nlev - 1; level >= 0; --level) {
+        const uint8_t* I = P.prev.base[level] + (size_t)pimg * P.prev.stride[level];
+        const uint8_t* J = P.next.base[level] + (size_t)nimg * P.next.stride[level];
+        const int w = P.prev.w[level], h = P.prev.h[level];
+        const int ipitch = P.prev.pitch[level], jpitch = P.next.pitch[level];
+        const int ilow = ((((unsigned long long)I) & 3ull) == 0 && (ipitch & 3) == 0) ? 0 : 4;   // see load12
+        const int jlow = ((((unsigned long long)J) & 3ull) == 0 && (jpitch & 3) == 0) ? 0 : 4;
+        const float sc = 1.f / (float)(1 << level);
+        const float ppx = ptx * sc, ppy = pty * sc;
+        if (level == P.nlev - 1) {
+            if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = nx * sc; ny = ny * sc; }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = nx * 2.f; ny = ny * 2.f; }
+        const float px = ppx - hwx, py = ppy - hwy;
+        const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+        if (ix < -winW || ix >= w || iy < -winH || iy >= h) {
+            if (level == 0) { st = false; errv = 0.f; }
+            continue;
+        }
+        float a = px - (float)ix, b = py - (float)iy;
+        int w00, w01, w10, w11;
+        bil_weights(a, b, w00, w01, w10, w11);
+        // ---- template ---------------------------------------------------------------------------------
+        // rows iy+r-1, iy+r, iy+r+1, bytes j=0..11 <-> columns ix+8hh-1+j
+        const bool ifast = ix - 1 >= ilow && ix + 8 + 15 <= w && iy - 1 >= 0 && iy + 16 < h;
+        const int X0 = ix - 1 + 8 * hh;
+        unsigned int A0, A1, A2, B0, B1, B2, C0, C1, C2;
+        load12(I, w, h, ipitch, X0, iy + r - 1, ifast, A0, A1, A2);
+        load12(I, w, h, ipitch, X0, iy + r, ifast, B0, B1, B2);
+        load12(I, w, h, ipitch, X0, iy + r + 1, ifast, C0, C1, C2);
+        int t0[11], t1[11];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+            int av = byte_of(A0, A1, A2, j), bv = byte_of(B0, B1, B2, j), cv = byte_of(C0, C1, C2, j);
+            t0[j] = 3 * (av + cv) + 10 * bv;
+            t1[j] = cv - av;
+        }
+        // Scharr at row iy+r, columns ix+8hh+k, k=0..8; zero outside the image (OpenCV pads derivatives with 0)
+        unsigned int D[9];
+        const bool rowin = (unsigned)(iy + r) < (unsigned)h;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            int gx = t0[k + 2] - t0[k];
+            int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
+            if (!ifast && !(rowin && (unsigned)(ix + 8 * hh + k) < (unsigned)w)) { gx = 0; gy = 0; }
+            D[k] = ((unsigned int)gx & 0xffffu) | ((unsigned int)gy << 16);
+        }
+        int Ip[8], Gx[8], Gy[8];
+        int iA11 = 0, iA12 = 0, iA22 = 0;
+        {
+            int gxa = (int)(short)(D[0] & 0xffffu), gya = (int)D[0] >> 16;
+            unsigned int Db = __shfl_down_sync(0xffffffffu, D[0], 2);
+            int gxc = (int)(short)(Db & 0xffffu), gyc = (int)Db >> 16;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int gxb = (int)(short)(D[k + 1] & 0xffffu), gyb = (int)D[k + 1] >> 16;
+                unsigned int Dn = __shfl_down_sync(0xffffffffu, D[k + 1], 2);
+                int gxd = (int)(short)(Dn & 0xffffu), gyd = (int)Dn >> 16;
+                int iv = (byte_of(B0, B1, B2, k + 1) * w00 + byte_of(B0, B1, B2, k + 2) * w01 +
+                          byte_of(C0, C1, C2, k + 1) * w10 + byte_of(C0, C1, C2, k + 2) * w11 + (1 << 8)) >> 9;
+                int gx = (gxa * w00 + gxb * w01 + gxc * w10 + gxd * w11 + (1 << 13)) >> 14;
+                int gy = (gya * w00 + gyb * w01 + gyc * w10 + gyd * w11 + (1 << 13)) >> 14;
+                if (!((vmask >> k) & 1u)) { gx = 0; gy = 0; }
+                Ip[k] = iv; Gx[k] = gx; Gy[k] = gy;
+                iA11 += gx * gx; iA12 += gx * gy; iA22 += gy * gy;
+                gxa = gxb; gya = gyb; gxc = gxd; gyc = gyd;
+            }
+        }
+        const float A11 = (float)warp_sum_ll(iA11) * FLT_SCALE;
+        const float A12 = (float)warp_sum_ll(iA12) * FLT_SCALE;
+        const float A22 = (float)warp_sum_ll(iA22) * FLT_SCALE;
+        float D2 = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = A11 - A22;
+        const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))) /
+                             (float)(2 * winW * winH);
+        if ((double)minEig < P.min_eig_thr || D2 < 1.1920928955078125e-7f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D2 = 1.f / D2;
+        float qx = nx - hwx, qy = ny - hwy;
+        float pdx = 0.f, pdy = 0.f;
+        bool lost = false;
+        for (int j = 0; j < P.max_count; ++j) {
+            const int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { lost = true; break; }
+            a = qx - (float)jx; b = qy - (float)jy;
+            bil_weights(a, b, w00, w01, w10, w11);
+            const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+            const bool jfast = jx >= jlow && jx + 8 + 16 <= w && jy >= 0 && jy + 15 < h;
+            unsigned int T0, T1, T2;
+            load12(J, w, h, jpitch, jx + 8 * hh, jy + r, jfast, T0, T1, T2);
+            const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
+                               U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+            int ib1 = 0, ib2 = 0;
+            LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
+                int diff = jv - Ip[k];
+                ib1 += diff * Gx[k]; ib2 += diff * Gy[k];
+            })
+            const float b1 = (float)warp_sum_ll(ib1) * FLT_SCALE;
+            const float b2 = (float)warp_sum_ll(ib2) * FLT_SCALE;
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D2);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D2);
+            qx += dx; qy += dy;
+            nx = qx + hwx; ny = qy + hwy;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (lost && level == 0) st = false;
+        if (st && level == 0) {
+            const float rx = nx - hwx, ry = ny - hwy;
+            const int jx = __float2int_rd(rx), jy = __float2int_rd(ry);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { st = false; }
+            else {
+                a = rx - (float)jx; b = ry - (float)jy;
+                bil_weights(a, b, w00, w01, w10, w11);
+                const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+                const bool jfast = jx >= jlow && jx + 8 + 16 <= w && jy >= 0 && jy + 15 < h;
+                unsigned int T0, T1, T2;
+                load12(J, w, h, jpitch, jx + 8 * hh, jy + r, jfast, T0, T1, T2);
+                const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
+                                   U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                int ie = 0;
+                LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
+                    if ((vmask >> k) & 1u) ie += abs(jv - Ip[k]);
+                })
+                errv = (float)warp_sum_ll(ie) * (1.f / (float)(32 * winW * winH));
+            }
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
+        status[po] = st ? 1 : 0;
+        if (err) err[po] = st ? errv : 0.f;
+    }
+}
+
 }  // namespace
 
 size_t ofb_lk_warp_smem(int win_w, int win_h)
@@ -269,6 +508,15 @@ int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_s
     P.flags = flags;
     P.prev_image0 = prev_image0; P.prev_image_step = prev_step;
     P.next_image0 = next_image0; P.next_image_step = next_step;
+    if (n_uniform <= 0) return OFB_OK;
+    const char* env = getenv("OFB_LK_GENERIC");      // parity tests cross-check the two kernels
+    if (win_w <= 16 && win_h <= 15 && !(env && env[0] == '1')) {
+        dim3 fgrid(ofb_div_up(n_uniform, LKF_WARPS), n_pairs);
+        lk_track_fast_kernel<<<fgrid, LKF_WARPS * 32, 0, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts,
+                                                                       counts_stride, n_uniform, pts_stride);
+        OFB_LAUNCH_CHECK(ctx);
+        return OFB_OK;
+    }
     size_t wsm = ofb_lk_warp_smem(win_w, win_h);
     size_t smem = wsm * LK_WARPS;
     static size_t lk_smem_set = 0;

@@ -227,3 +227,43 @@ def test_lk_live_cv2_1080p(ctx):
     assert ok.sum() >= 900
     assert np.abs(n - rn)[ok].max() <= 0.05
     assert np.median(np.abs(n - rn)[ok]) <= 1e-3
+
+
+def test_two_kernel_variants_agree(ctx):
+    """The tile lambda_min kernel and the generic one build the map from the same exact integer sums:
+    bit-identical maps; the register-resident LK kernel and the generic shared-memory one: identical
+    status, positions equal to fp32 rounding (both accumulate the same integers exactly)."""
+    import ofb200
+    for (h, w), seed in [((240, 320), 21), ((131, 517), 22), ((480, 640), 23)]:
+        img = synth.texture(h, w, seed)
+        for bs in (3, 7, 12, 32):
+            fast = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
+            os.environ["OFB_EIG_GENERIC"] = "1"
+            try:
+                gen = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
+                pts_gen = ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx)
+            finally:
+                os.environ["OFB_EIG_GENERIC"] = "0"
+            assert np.array_equal(fast, gen), (h, w, bs, np.abs(fast - gen).max())
+            pts_fast = ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx)
+            assert np.array_equal(as_list(pts_fast), as_list(pts_gen))
+    for case in range(3):
+        a, b = synth.affine_pair(240, 320, 30 + case, shift=(3.5 + case, -2.25), rot=0.01 * case)
+        pts = io.good_features(a, 150, 0.01, 8, block_size=7)
+        extra = np.array([[0, 0], [2.5, 3.5], [319, 239], [318.2, 5.3], [4, 237.5], [160, 0.4], [0.2, 120]], np.float32).reshape(-1, 1, 2)
+        pts = np.concatenate([pts, extra])
+        for win in ((15, 15), (9, 13), (16, 15)):
+            kw = dict(winSize=win, maxLevel=3, criteria=(3, 20, 0.03))
+            n1, s1, e1 = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, ctx=ctx, **kw)
+            os.environ["OFB_LK_GENERIC"] = "1"
+            try:
+                n2, s2, e2 = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, ctx=ctx, **kw)
+            finally:
+                os.environ["OFB_LK_GENERIC"] = "0"
+            assert np.array_equal(s1, s2), (case, win)
+            ok = s1.ravel() == 1
+            assert np.abs(n1 - n2)[ok].max() <= 1e-4, (case, win, np.abs(n1 - n2)[ok].max())
+            assert np.abs(e1 - e2)[ok].max() <= 1e-4
+            on, os_, oe = io.pyrlk(a, b, pts, win, 3, (3, 20, 0.03))
+            assert np.array_equal(s1, os_)
+            assert np.abs(n1 - on)[ok].max() <= 5e-3
