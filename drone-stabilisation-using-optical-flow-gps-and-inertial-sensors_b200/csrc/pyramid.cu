@@ -29,6 +29,15 @@ __device__ __forceinline__ int refl101(int p, int len)
     return p;
 }
 
+// Branch-free reflect-101 + clamp: exact wherever one reflection suffices (|overshoot| < len), which covers
+// every source position a needed output reads when len >= 3; positions beyond that are never consumed.
+__device__ __forceinline__ int refl101_bf(int p, int len)
+{
+    p = p < 0 ? -p : p;
+    p = p >= len ? 2 * len - 2 - p : p;
+    return max(0, min(p, len - 1));
+}
+
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride,
                 uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride)
@@ -38,21 +47,36 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, siz
     uint8_t* d = dst + (size_t)blockIdx.z * dstride;
     const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
     const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;   // source coordinate of tile[0][0]
-    const bool interior = sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh &&
-                          ((spitch & 15) == 0) && ((((size_t)s) & 15) == 0);
-    if (interior) {
-        const uint4* s128 = (const uint4*)(s + (size_t)sy0 * spitch + sx0);
-        const int qpitch = spitch >> 4;
+    // Staging in 16-byte groups: a group that lies inside its (reflected) source row is one 128-bit load;
+    // only groups that cross the image edge gather 16 bytes with reflect-101 (independent loads, so a
+    // border tile costs one memory latency, not one per byte).
+    const bool aligned = ((spitch & 15) == 0) && ((((size_t)s) & 15) == 0);
+    const bool tiny = sw < 4 || sh < 4;
+    {
         uint4* t128 = (uint4*)tile;
-        for (int i = threadIdx.x; i < PS_H * (PS_W / 16); i += 256) {
-            int r = i / (PS_W / 16), c = i - r * (PS_W / 16);
-            t128[r * (PS_PITCH / 16) + c] = __ldg(s128 + (size_t)r * qpitch + c);
-        }
-    } else {
-        for (int i = threadIdx.x; i < PS_H * PS_W; i += 256) {
-            int r = i / PS_W, c = i - r * PS_W;
-            int yy = refl101(sy0 + r, sh), xx = refl101(sx0 + c, sw);
-            tile[r * PS_PITCH + c] = __ldg(s + (size_t)yy * spitch + xx);
+        constexpr int GPR = PS_W / 16;                 // groups per row
+        for (int i = threadIdx.x; i < PS_H * GPR; i += 256) {
+            const int r = i / GPR, c = i - r * GPR;
+            const int yy = tiny ? refl101(sy0 + r, sh) : refl101_bf(sy0 + r, sh);
+            const int gx0 = sx0 + 16 * c;
+            const uint8_t* row = s + (size_t)yy * spitch;
+            uint4 v;
+            if (aligned && gx0 >= 0 && gx0 + 16 <= sw) {
+                v = __ldg((const uint4*)(row + gx0));
+            } else {
+                unsigned int wv[4] = {0, 0, 0, 0};
+                if (tiny) {
+                    for (int j = 0; j < 16; ++j) wv[j >> 2] |= (unsigned int)__ldg(row + refl101(gx0 + j, sw)) << (8 * (j & 3));
+                } else {
+                    unsigned int bv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) bv[j] = __ldg(row + refl101_bf(gx0 + j, sw));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) wv[j >> 2] |= bv[j] << (8 * (j & 3));
+                }
+                v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            }
+            t128[r * (PS_PITCH / 16) + c] = v;
         }
     }
     __syncthreads();
