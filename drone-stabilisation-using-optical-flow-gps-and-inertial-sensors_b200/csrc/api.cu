@@ -57,7 +57,13 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (ofb_pyr* p : ctx->pyramids) { cudaFree(p->base); delete p; }
-    for (int i = 0; i < 2; ++i) if (ctx->pair_pyr[i]) { cudaFree(ctx->pair_pyr[i]->base); delete ctx->pair_pyr[i]; }
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < 2; ++i) if (ctx->pair_pyr[s][i]) { cudaFree(ctx->pair_pyr[s][i]->base); delete ctx->pair_pyr[s][i]; }
+    for (int s = 0; s < 2; ++s) {
+        if (ctx->ev_ready[s]) cudaEventDestroy(ctx->ev_ready[s]);
+        if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < OFB_NSCRATCH; ++i) ctx->scratch[i].release();
     for (int i = 0; i < 4; ++i) ctx->pin[i].release();
     for (int i = 0; i < OFB_NSTAGE_EV; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);

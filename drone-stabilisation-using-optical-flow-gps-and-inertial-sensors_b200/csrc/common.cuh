@@ -82,7 +82,11 @@ struct ofb_ctx {
     DevBuf scratch[OFB_NSCRATCH];   // role-indexed scratch arenas (see each stage)
     PinBuf pin[4];
     std::vector<ofb_pyr*> pyramids;
-    ofb_pyr* pair_pyr[2] = {nullptr, nullptr};   // workspace pyramids of ofb_frame_pairs
+    ofb_pyr* pair_pyr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [slot][prev|next] workspace pyramids of ofb_frame_pairs
+    // host-input pipelining of ofb_frame_pairs: H2D of sub-batch i+1 on copy_stream overlaps compute of sub-batch i
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t upload_stream = nullptr;        // stream level-0 uploads go to (nullptr = stream)
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // optional per-stage CUDA-event timing of ofb_frame_pairs (ofb_ctx_set_profile)
     bool profile = false;
     cudaEvent_t stage_ev[OFB_NSTAGE_EV] = {};
@@ -99,7 +103,8 @@ enum {
 };
 
 struct ofb_pyr {
-    int n_images = 0, n_levels = 0;
+    int n_images = 0, n_levels = 0;       // n_images = capacity
+    int n_active = 0;                     // images in use (<= n_images): launches and uploads cover these
     int w[OFB_MAX_LEVELS], h[OFB_MAX_LEVELS], pitch[OFB_MAX_LEVELS];
     size_t level_off[OFB_MAX_LEVELS];     // byte offset of level l (image 0) inside `base`
     size_t image_stride[OFB_MAX_LEVELS];  // byte stride between images at level l
@@ -168,4 +173,4 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* pyr);
 int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
                   int max_level, ofb_pyr** out);
 int ofb_pyr_prepare(ofb_ctx* ctx, ofb_pyr** slot, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
-                    int n_images, int max_level);
+                    int n_images, int capacity, int max_level, bool build);

@@ -47,6 +47,44 @@ pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict_
 
 }  // namespace
 
+// Stages 1b-4 for pairs [c0, c0+n) whose level-0 frames already sit in pp/pn (images 0..n-1 of each).
+static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, ofb_pyr* pn, int n, int c0,
+                           const ofb_imu_sample* dimu, const int* counts_in, float* d_prev, float* d_next, uint8_t* d_stat,
+                           ofb_pair_result* d_res, bool mark)
+{
+    const int w = cfg->width, h = cfg->height, K = cfg->max_corners;
+#define STAGE_MARK(i) do { if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream)); } while (0)
+    STAGE_MARK(0);
+    OFB_TRY(ofb_pyr_build_device(ctx, pp));
+    OFB_TRY(ofb_pyr_build_device(ctx, pn));
+    STAGE_MARK(1);
+    float* cp = d_prev + (size_t)c0 * 2 * K;
+    float* cn = d_next + (size_t)c0 * 2 * K;
+    uint8_t* cs = d_stat + (size_t)c0 * K;
+    const int* counts; int counts_stride;
+    if (cfg->detect) {
+        FeatImageState* st = nullptr;
+        unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
+        OFB_TRY(ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n, nullptr, 0, 0, K,
+                                    cfg->quality, cfg->min_distance, cfg->block_size, cand_cap, cp, (size_t)2 * K, K, &st));
+        counts = &st->n_out; counts_stride = (int)(sizeof(FeatImageState) / sizeof(int));
+    } else {
+        if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[2], ctx->stream));
+        counts = counts_in + c0; counts_stride = 1;
+    }
+    STAGE_MARK(3);
+    OFB_TRY(ctx->scratch[SC_ERR].reserve(sizeof(float) * (size_t)n * K));
+    OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, 0, 1, n, cp, counts, counts_stride, K, (size_t)K, cfg->win_w, cfg->win_h,
+                          cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, cn, cs, ctx->scratch[SC_ERR].as<float>()));
+    STAGE_MARK(4);
+    TrackLoader ld{cp, cn, cs, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
+    pair_solve_kernel<<<n, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, dimu + c0, d_res + c0);
+    OFB_LAUNCH_CHECK(ctx);
+    STAGE_MARK(5);
+#undef STAGE_MARK
+    return OFB_OK;
+}
+
 extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pairs,
                                const uint8_t* prev, const uint8_t* next, int pitch, size_t image_stride,
                                const ofb_imu_sample* imu, const float* pts_in, const int* n_in,
@@ -62,14 +100,7 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     OFB_REQUIRE(cfg->detect || (pts_in && n_in), "frame_pairs: detect==0 needs pts_in and n_in");
     OFB_REQUIRE(n_pairs == 1 || image_stride >= (size_t)pitch * (h - 1) + w, "frame_pairs: image_stride too small");
     OFB_CUDA(cudaSetDevice(ctx->device));
-#define STAGE_MARK(i) do { if (ctx->profile) OFB_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream)); } while (0)
-    // stage 1: both pyramids (levels >= 1); host frames are copied into the workspace level 0
-    STAGE_MARK(0);
-    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0], prev, w, h, pitch, image_stride, n_pairs, cfg->max_level));
-    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[1], next, w, h, pitch, image_stride, n_pairs, cfg->max_level));
-    ofb_pyr* pp = ctx->pair_pyr[0];
-    ofb_pyr* pn = ctx->pair_pyr[1];
-    size_t npts = (size_t)n_pairs * K;
+    const size_t npts = (size_t)n_pairs * K;
     OutStage o[4];
     OFB_TRY(ofb_stage_out(ctx, SC_PTS0, prev_pts, sizeof(float) * 2 * npts, &o[0]));
     OFB_TRY(ofb_stage_out(ctx, SC_PTS1, next_pts, sizeof(float) * 2 * npts, &o[1]));
@@ -80,55 +111,64 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     if (!d_prev) { OFB_TRY(ctx->scratch[SC_PTS0].reserve(sizeof(float) * 2 * npts)); d_prev = ctx->scratch[SC_PTS0].as<float>(); }
     if (!d_next) { OFB_TRY(ctx->scratch[SC_PTS1].reserve(sizeof(float) * 2 * npts)); d_next = ctx->scratch[SC_PTS1].as<float>(); }
     if (!d_stat) { OFB_TRY(ctx->scratch[SC_STAT].reserve(npts)); d_stat = ctx->scratch[SC_STAT].as<uint8_t>(); }
-    STAGE_MARK(1);
     const void* dimu;
     OFB_TRY(ofb_stage_in(ctx, SC_IN3, imu, sizeof(ofb_imu_sample) * n_pairs, &dimu));
-    const int* counts; int counts_stride;
-    if (cfg->detect) {
-        // stage 2 on level 0 of the previous frames
-        FeatImageState* st = nullptr;
-        unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
-        OFB_TRY(ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n_pairs, nullptr, 0, 0, K,
-                                    cfg->quality, cfg->min_distance, cfg->block_size, cand_cap, d_prev, (size_t)2 * K, K,
-                                    &st));
-        counts = &st->n_out; counts_stride = (int)(sizeof(FeatImageState) / sizeof(int));
-    } else {
-        const void *dp, *dn;
+    const int* counts_in = nullptr;
+    if (!cfg->detect) {
+        const void* dn;
         OFB_TRY(ofb_stage_in(ctx, SC_IN4, n_in, sizeof(int) * n_pairs, &dn));
-        if (ofb_is_device_ptr(pts_in)) {
-            if ((const float*)pts_in != d_prev)
-                OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyDeviceToDevice, ctx->stream));
-        } else {
-            OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        (void)dp;
-        counts = (const int*)dn; counts_stride = 1;
+        counts_in = (const int*)dn;
+        if ((const float*)pts_in != d_prev)
+            OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyDefault, ctx->stream));
     }
-    // stage 3
-    STAGE_MARK(3);
-    OFB_TRY(ctx->scratch[SC_ERR].reserve(sizeof(float) * npts));
-    OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, 0, 1, n_pairs, d_prev, counts, counts_stride, K, (size_t)K, cfg->win_w,
-                          cfg->win_h, cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, d_next, d_stat,
-                          ctx->scratch[SC_ERR].as<float>()));
-    // stage 4
-    STAGE_MARK(4);
-    TrackLoader ld{d_prev, d_next, d_stat, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
-    pair_solve_kernel<<<n_pairs, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, (const ofb_imu_sample*)dimu,
-                                                                     (ofb_pair_result*)o[3].dev);
-    OFB_LAUNCH_CHECK(ctx);
-    STAGE_MARK(5);
+    const bool host_frames = !ofb_is_device_ptr(prev) && !ofb_is_device_ptr(next);
+    const int chunk = 8;
+    if (host_frames && n_pairs > chunk && !ctx->profile) {
+        // Host frames: pipeline sub-batches. The H2D copy of sub-batch i+1 runs on copy_stream into the other
+        // workspace slot while sub-batch i computes on the context stream.
+        if (!ctx->copy_stream) {
+            OFB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int s = 0; s < 2; ++s) {
+                OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[s], cudaEventDisableTiming));
+                OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
+            }
+        }
+        // copies must not start before earlier work on the context stream that may still read the slots
+        OFB_CUDA(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+        OFB_CUDA(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+        int ci = 0;
+        for (int c0 = 0; c0 < n_pairs; c0 += chunk, ++ci) {
+            const int n = n_pairs - c0 < chunk ? n_pairs - c0 : chunk;
+            const int slot = ci & 1;
+            OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));
+            ctx->upload_stream = ctx->copy_stream;
+            int r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
+                                    chunk, cfg->max_level, false);
+            if (r == OFB_OK)
+                r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
+                                    chunk, cfg->max_level, false);
+            ctx->upload_stream = nullptr;
+            OFB_TRY(r);
+            OFB_CUDA(cudaEventRecord(ctx->ev_ready[slot], ctx->copy_stream));
+            OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[slot], 0));
+            OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[slot][0], ctx->pair_pyr[slot][1], n, c0, (const ofb_imu_sample*)dimu,
+                                    counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
+            OFB_CUDA(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+        }
+        return ofb_finish_out(ctx, o, 4);
+    }
+    // resident frames (or a small batch): one pass over the whole batch
+    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][0], prev, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
+    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][1], next, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
+    OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[0][0], ctx->pair_pyr[0][1], n_pairs, 0, (const ofb_imu_sample*)dimu, counts_in,
+                            d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, ctx->profile));
     int rc = ofb_finish_out(ctx, o, 4);
     if (rc == OFB_OK && ctx->profile) {
-        // stage order: 0 pyramids (+H2D of host frames), 1 lambda_min+NMS, 2 ordered selection, 3 LK, 4 solve
+        // stage order: 0 pyramids, 1 lambda_min+NMS, 2 ordered selection, 3 LK, 4 solve
         OFB_CUDA(cudaEventSynchronize(ctx->stage_ev[5]));
         for (int i = 0; i < OFB_NSTAGES; ++i) {
             float ms = 0.f;
-            if (cfg->detect || (i != 1 && i != 2)) {
-                int e0 = i, e1 = i + 1;
-                if (!cfg->detect && i == 0) e1 = 1;
-                if (!cfg->detect && i == 3) e0 = 3;
-                OFB_CUDA(cudaEventElapsedTime(&ms, ctx->stage_ev[e0], ctx->stage_ev[e1]));
-            }
+            OFB_CUDA(cudaEventElapsedTime(&ms, ctx->stage_ev[i], ctx->stage_ev[i + 1]));
             ctx->stage_ms[i] += ms;
         }
         ctx->stage_calls++;

@@ -135,7 +135,7 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         const uint8_t* s; int sp; size_t ss;
         if (l == 1) { s = p->level0; sp = p->level0_pitch; ss = p->level0_stride; }
         else { s = p->base + p->level_off[l - 1]; sp = p->pitch[l - 1]; ss = p->image_stride[l - 1]; }
-        dim3 grid(ofb_div_up(p->w[l], PT_W), ofb_div_up(p->h[l], PT_H), p->n_images);
+        dim3 grid(ofb_div_up(p->w[l], PT_W), ofb_div_up(p->h[l], PT_H), p->n_active);
         pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss,
                                                        p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
                                                        p->image_stride[l]);
@@ -146,20 +146,21 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
 
 static int pyr_upload_level0(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* img, int pitch, size_t image_stride)
 {
-    for (int i = 0; i < p->n_images; ++i)
+    cudaStream_t s = ctx->upload_stream ? ctx->upload_stream : ctx->stream;
+    for (int i = 0; i < p->n_active; ++i)
         OFB_CUDA(cudaMemcpy2DAsync(p->base + p->level_off[0] + (size_t)i * p->image_stride[0], p->pitch[0],
-                                   img + (size_t)i * image_stride, pitch, p->w[0], p->h[0], cudaMemcpyHostToDevice,
-                                   ctx->stream));
+                                   img + (size_t)i * image_stride, pitch, p->w[0], p->h[0], cudaMemcpyHostToDevice, s));
     return OFB_OK;
 }
 
 // Allocates the pyramid object and its level storage. When `img` is device memory level 0 aliases
 // it (the caller keeps it alive while the pyramid is in use); host images are copied in.
-int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
-                  int max_level, ofb_pyr** out)
+static int ofb_pyr_alloc_cap(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_active,
+                             int n_images, int max_level, ofb_pyr** out)
 {
     ofb_pyr* p = new ofb_pyr();
     p->n_images = n_images;
+    p->n_active = n_active;
     bool dev = ofb_is_device_ptr(img);
     int lw = w, lh = h, nl = 1;
     p->w[0] = w; p->h[0] = h;
@@ -196,24 +197,34 @@ int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, siz
     return OFB_OK;
 }
 
-// Workspace pyramid for the fused path: reuses *slot when geometry and residency match, so a steady
-// stream of frame pairs never reallocates.
+int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
+                  int max_level, ofb_pyr** out)
+{
+    return ofb_pyr_alloc_cap(ctx, img, w, h, pitch, image_stride, n_images, n_images, max_level, out);
+}
+
+// Workspace pyramid for the fused path: reuses *slot when geometry and residency match (capacity >= n_images),
+// so a steady stream of frame pairs never reallocates. build=false only refreshes level 0 (upload on
+// ctx->upload_stream when set); the caller then runs ofb_pyr_build_device on the compute stream.
 int ofb_pyr_prepare(ofb_ctx* ctx, ofb_pyr** slot, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
-                    int n_images, int max_level)
+                    int n_images, int capacity, int max_level, bool build)
 {
     ofb_pyr* p = *slot;
     bool dev = ofb_is_device_ptr(img);
+    if (capacity < n_images) capacity = n_images;
     int want_levels = 1; { int lw = w, lh = h; for (int l = 1; l <= max_level && l < OFB_MAX_LEVELS; ++l) { lw = (lw + 1) / 2; lh = (lh + 1) / 2; want_levels = l + 1; if (lw == 1 && lh == 1) break; } }
-    if (p && p->n_images == n_images && p->w[0] == w && p->h[0] == h && p->n_levels == want_levels &&
-        p->level0_owned == !dev) {
+    if (p && p->n_images >= n_images && p->n_images <= 2 * capacity && p->w[0] == w && p->h[0] == h &&
+        p->n_levels == want_levels && p->level0_owned == !dev) {
+        p->n_active = n_images;
         if (dev) { p->level0 = img; p->level0_pitch = pitch; p->level0_stride = image_stride; p->pitch[0] = pitch; p->image_stride[0] = image_stride; }
         else OFB_TRY(pyr_upload_level0(ctx, p, img, pitch, image_stride));
     } else {
-        if (p) { cudaStreamSynchronize(ctx->stream); cudaFree(p->base); delete p; *slot = nullptr; }
-        OFB_TRY(ofb_pyr_alloc(ctx, img, w, h, pitch, image_stride, n_images, max_level, &p));
+        if (p) { cudaDeviceSynchronize(); cudaFree(p->base); delete p; *slot = nullptr; }
+        // allocate for `capacity` images, use n_images of them
+        OFB_TRY(ofb_pyr_alloc_cap(ctx, img, w, h, pitch, image_stride, n_images, capacity, max_level, &p));
         *slot = p;
     }
-    return ofb_pyr_build_device(ctx, p);
+    return build ? ofb_pyr_build_device(ctx, p) : OFB_OK;
 }
 
 extern "C" int ofb_pyramid(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride,

@@ -267,3 +267,32 @@ def test_overlap(ctx):
         assert ofb200.overlap(a, b, ctx=ctx) == vo.overlap(a, b)
     a = np.array([1.0, 2.0, 2.0, 3.0]); b = np.array([3.0, 3.0, 1.0])
     assert ofb200.overlap(a, b, ctx=ctx) == vo.overlap(a, b)
+
+
+def test_frame_pairs_pipelined_host_path_equals_resident(ctx):
+    """Host frames in batches > 8 go through the copy/compute pipeline (sub-batches, two workspace slots);
+    results must be identical to the same pairs processed one small batch at a time and to the resident path."""
+    import ofb200
+    import torch
+    frames = [synth.make_pair(120, 160, s % 5, s, max_disp=4.0) for s in range(19)]
+    a = np.stack([f[0] for f in frames]); b = np.stack([f[1] for f in frames])
+    mo0 = frames[0][2]
+    K = 48
+    cfg = ofb200.make_pair_cfg(160, 120, K, 0.01, 6, 5, (15, 15), 2, (3, 20, 0.03), variant="node",
+                               principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"], flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
+    imu = np.zeros(len(frames), ofb200._lib.IMU_DTYPE)
+    for i, f in enumerate(frames):
+        imu["d"][i], imu["n"][i], imu["w"][i] = f[2]["d"], f[2]["n"], f[2]["w"]
+    for rep in range(2):          # twice: the second call reuses the workspace slots
+        res, pp, pn, st = ofb200.frame_pairs(a, b, imu, cfg, want_tracks=True, ctx=ctx)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    torch.cuda.synchronize()
+    res_d, pp_d, pn_d, st_d = ofb200.frame_pairs(ta, tb, imu, cfg, want_tracks=True, ctx=ctx)
+    for name in ("v", "s", "res", "rank", "n_features", "n_tracked"):
+        assert np.array_equal(res[name], res_d[name]), name
+    assert np.array_equal(pp, pp_d) and np.array_equal(pn, pn_d) and np.array_equal(st, st_d)
+    for i0 in (0, 8, 16):
+        sl = slice(i0, min(i0 + 5, len(frames)))
+        r1, p1, n1, s1 = ofb200.frame_pairs(a[sl], b[sl], imu[sl], cfg, want_tracks=True, ctx=ctx)
+        assert np.array_equal(r1["v"], res["v"][sl]) and np.array_equal(n1, pn[sl]) and np.array_equal(s1, st[sl])
+    assert (res["n_tracked"] > 10).all()
