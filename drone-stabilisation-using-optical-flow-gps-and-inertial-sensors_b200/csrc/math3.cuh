@@ -10,11 +10,8 @@
 // ---- Philox4x32-10 (Salmon et al., SC'11) ------------------------------------------------------
 OFB_HD void ofb_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
 {
-#ifdef __CUDA_ARCH__
-    lo = a * b; hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
-#endif
+    uint64_t p = (uint64_t)a * b;          // one IMAD.WIDE.U32 on the device
+    lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
 }
 
 OFB_HD uint4 ofb_philox4x32_10(uint4 c, uint2 k)

@@ -147,6 +147,11 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
 static int pyr_upload_level0(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* img, int pitch, size_t image_stride)
 {
     cudaStream_t s = ctx->upload_stream ? ctx->upload_stream : ctx->stream;
+    if (pitch == p->pitch[0] && image_stride == p->image_stride[0]) {       // same layout on both sides: one copy
+        OFB_CUDA(cudaMemcpyAsync(p->base + p->level_off[0], img, image_stride * (size_t)(p->n_active - 1) +
+                                 (size_t)pitch * (p->h[0] - 1) + p->w[0], cudaMemcpyHostToDevice, s));
+        return OFB_OK;
+    }
     for (int i = 0; i < p->n_active; ++i)
         OFB_CUDA(cudaMemcpy2DAsync(p->base + p->level_off[0] + (size_t)i * p->image_stride[0], p->pitch[0],
                                    img + (size_t)i * image_stride, pitch, p->w[0], p->h[0], cudaMemcpyHostToDevice, s));
@@ -173,7 +178,9 @@ static int ofb_pyr_alloc_cap(ofb_ctx* ctx, const uint8_t* img, int w, int h, int
     size_t off = 0;
     for (int l = 0; l < nl; ++l) {
         if (l == 0 && dev) { p->pitch[0] = pitch; p->level_off[0] = 0; p->image_stride[0] = image_stride; continue; }
-        p->pitch[l] = (int)align_up((size_t)p->w[l] + 4, 16);
+        // level 0 (host frames copied in): tight 16-aligned pitch, so that frames whose width is a multiple
+        // of 16 and whose size is a multiple of 256 land with ONE contiguous H2D copy per sub-batch
+        p->pitch[l] = (int)align_up((size_t)p->w[l] + (l == 0 ? 0 : 4), 16);
         p->image_stride[l] = align_up((size_t)p->pitch[l] * p->h[l], 256);
         p->level_off[l] = off;
         off += p->image_stride[l] * n_images;
