@@ -293,7 +293,7 @@ __device__ __forceinline__ float warp_sum_f(float v)
         }                                                                                         \
     }
 
-__global__ void __launch_bounds__(LKF_WARPS * 32)
+__global__ void __launch_bounds__(LKF_WARPS * 32, 8)
 lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                      uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
                      int counts_stride, int n_uniform, size_t pts_stride)
@@ -418,8 +418,10 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                 int diff = jv - Ip[k];
                 ib1 += diff * Gx[k]; ib2 += diff * Gy[k];
             })
-            const float b1 = (float)warp_sum_ll(ib1) * FLT_SCALE;
-            const float b2 = (float)warp_sum_ll(ib2) * FLT_SCALE;
+            // per-lane partial sums are exact int32; the cross-lane sum is a fixed-order fp32 butterfly (OpenCV
+            // accumulates the same integers in fp32 as well): half the shuffles of the exact 64-bit reduction
+            const float b1 = warp_sum_f((float)ib1) * FLT_SCALE;
+            const float b2 = warp_sum_f((float)ib2) * FLT_SCALE;
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D2);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D2);
             qx += dx; qy += dy;
