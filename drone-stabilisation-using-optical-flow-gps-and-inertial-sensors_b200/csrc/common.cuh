@@ -87,6 +87,11 @@ struct ofb_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t upload_stream = nullptr;        // stream level-0 uploads go to (nullptr = stream)
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // the ordered-selection kernel occupies one CTA per image; the pyramid kernels of the same batch run beside
+    // it on aux_stream (fork after the lambda_min kernel, join before LK)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_after_eig = false;                 // ofb_features_device records ev_fork after the lambda_min launch
     // optional per-stage CUDA-event timing of ofb_frame_pairs (ofb_ctx_set_profile)
     bool profile = false;
     cudaEvent_t stage_ev[OFB_NSTAGE_EV] = {};

@@ -110,10 +110,10 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
     R_out = sqrt((double)accR / lmin) + P.baseR;
 }
 
-// fp32 variant: 5 CTAs/SM (96 registers, 20 warps) -- the kernel is issue/dependency bound and gains from
-// the extra warps; the fp64 variant needs its 190 registers.
+// Register budget left to the compiler (128 for fp32): forcing 5 CTAs/SM (96 registers) was measured slower
+// (2.19e9 vs 2.40e9 trials/s) -- the spills cost more than the extra warps gain.
 template <class T>
-__global__ void __launch_bounds__(MC_THREADS, (sizeof(T) == 4 ? 5 : 2))
+__global__ void __launch_bounds__(MC_THREADS)
 mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const double* __restrict__ pos,
                 const double* __restrict__ flow, uint64_t trial_begin, uint64_t trials, uint2 key,
                 double* __restrict__ partials, double* __restrict__ v_dump, double* __restrict__ R_dump)

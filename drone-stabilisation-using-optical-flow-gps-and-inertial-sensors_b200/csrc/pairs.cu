@@ -54,9 +54,19 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
 {
     const int w = cfg->width, h = cfg->height, K = cfg->max_corners;
 #define STAGE_MARK(i) do { if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream)); } while (0)
+    // Detection only needs level 0, and the selection kernel keeps just one SM per image busy: unless stage
+    // timing is on, the pyramids are built on aux_stream while the selection runs (fork after lambda_min).
+    const bool overlap = cfg->detect && !mark;
+    if (overlap && !ctx->aux_stream) {
+        OFB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
     STAGE_MARK(0);
-    OFB_TRY(ofb_pyr_build_device(ctx, pp));
-    OFB_TRY(ofb_pyr_build_device(ctx, pn));
+    if (!overlap) {
+        OFB_TRY(ofb_pyr_build_device(ctx, pp));
+        OFB_TRY(ofb_pyr_build_device(ctx, pn));
+    }
     STAGE_MARK(1);
     float* cp = d_prev + (size_t)c0 * 2 * K;
     float* cn = d_next + (size_t)c0 * 2 * K;
@@ -65,9 +75,24 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
     if (cfg->detect) {
         FeatImageState* st = nullptr;
         unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
-        OFB_TRY(ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n, nullptr, 0, 0, K,
-                                    cfg->quality, cfg->min_distance, cfg->block_size, cand_cap, cp, (size_t)2 * K, K, &st));
+        ctx->fork_after_eig = overlap;
+        int fr = ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n, nullptr, 0, 0, K,
+                                     cfg->quality, cfg->min_distance, cfg->block_size, cand_cap, cp, (size_t)2 * K, K, &st);
+        ctx->fork_after_eig = false;
+        OFB_TRY(fr);
         counts = &st->n_out; counts_stride = (int)(sizeof(FeatImageState) / sizeof(int));
+        if (overlap) {
+            // aux_stream: wait for the lambda_min kernel, build both pyramids beside the selection kernel
+            OFB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->aux_stream;
+            int pr = ofb_pyr_build_device(ctx, pp);
+            if (pr == OFB_OK) pr = ofb_pyr_build_device(ctx, pn);
+            ctx->stream = main_stream;
+            OFB_TRY(pr);
+            OFB_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        }
     } else {
         if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[2], ctx->stream));
         counts = counts_in + c0; counts_stride = 1;

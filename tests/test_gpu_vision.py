@@ -262,8 +262,10 @@ def test_two_kernel_variants_agree(ctx):
                 os.environ["OFB_LK_GENERIC"] = "0"
             assert np.array_equal(s1, s2), (case, win)
             ok = s1.ravel() == 1
-            assert np.abs(n1 - n2)[ok].max() <= 1e-4, (case, win, np.abs(n1 - n2)[ok].max())
-            assert np.abs(e1 - e2)[ok].max() <= 1e-4
+            # the fast kernel sums the per-lane int32 partials of the mismatch vector in fp32 (as OpenCV does);
+            # the generic one sums them exactly: they agree to fp32 rounding, far inside the 0.05 px contract
+            assert np.abs(n1 - n2)[ok].max() <= 1e-3, (case, win, np.abs(n1 - n2)[ok].max())
+            assert np.abs(e1 - e2)[ok].max() <= 1e-3
             on, os_, oe = io.pyrlk(a, b, pts, win, 3, (3, 20, 0.03))
             assert np.array_equal(s1, os_)
             assert np.abs(n1 - on)[ok].max() <= 5e-3
