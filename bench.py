@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-pairs", type=int, default=4, help="pairs per step of the reference arm")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default, the headline line); c4 = 3840x2160 single-pair latency; c5 = 256-stream 720p fleet")
     return ap.parse_args()
 
 
@@ -184,10 +186,82 @@ def mc_workload(ofb200, trials_total):
     return steps, np.vstack(pos), np.vstack(flow), per_step
 
 
+def extra_workload(args):
+    """BASELINE configs 4 and 5 (not the headline line): C4 = 3840x2160, 5000 features, maxLevel 5, per-pair p50
+    latency of one resident pair; C5 = 256 concurrent 1280x720 streams, 500 features, maxLevel 3, streams
+    sharded over the ranks, aggregate pairs/s. One JSON line each."""
+    import ctypes as C
+    import torch
+    import ofb200
+    import synth
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = ofb200.Context(local)
+    if args.workload == "c4":
+        w, h, feat, ml, B, distinct = 3840, 2160, 5000, 5, 1, 2
+    else:
+        w, h, feat, ml, distinct = 1280, 720, 500, 3, 8
+        B = 256 // world + (1 if rank < 256 % world else 0)
+    pairs = [synth.make_pair(h, w, stream_id=rank, pair_id=1000 * rank + i) for i in range(distinct)]
+    mo0 = pairs[0][2]
+    cfg = ofb200.make_pair_cfg(w, h, feat, QUALITY, MIN_DIST, BLOCK, WIN, ml, CRIT, variant="node",
+                               principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"], flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
+    imu = imu_array(ofb200, pairs, B)
+    a = torch.from_numpy(np.stack([pairs[i % distinct][0] for i in range(B)])).cuda()
+    b = torch.from_numpy(np.stack([pairs[i % distinct][1] for i in range(B)])).cuda()
+    d_imu = torch.from_numpy(imu.view(np.uint8).reshape(-1).copy()).cuda()
+    d_res = torch.zeros(B * ofb200._lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    P = ofb200._lib.ptr
+
+    def step():
+        ofb200._lib.check(ctx.lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, P(a), P(b), w, w * h, P(d_imu), None, None, P(d_res),
+                                                  None, None, None))
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    if args.workload == "c4":
+        lat = []
+        for _ in range(max(args.steps, 50)):
+            ctx.timer_start(); step(); lat.append(ctx.timer_stop())
+        res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
+        lat = np.array(lat)
+        line = {"metric": "3840x2160 frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
+                "unit": "ms", "p95": float(np.percentile(lat, 95)), "n_gpus": 1, "steps": len(lat), "higher_is_better": False,
+                "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call"},
+                "check": {"n_tracked": int(res["n_tracked"][0]), "v": res["v"][0].tolist(), "truth": pairs[0][2]["v"].tolist()}}
+    else:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            step()
+        ms = ctx.timer_stop()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
+        line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "config": {"workload": "C5: 256 streams x 1280x720, 500 features, maxLevel 3, stream-sharded", "streams_per_gpu": B},
+                "check": {"min_tracked": int(res["n_tracked"].min())}}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload != "c2":
+        return extra_workload(args)
     import torch
     import ofb200
     rank = int(os.environ.get("RANK", "0"))
