@@ -234,7 +234,13 @@ def extra_workload(args):
             ctx.timer_start(); step(); lat.append(ctx.timer_stop())
         res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
         lat = np.array(lat)
+        ctx.set_profile(True)
+        for _ in range(10):
+            step()
+        sms, calls = ctx.stage_times()
+        ctx.set_profile(False)
         line = {"metric": "3840x2160 frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
+                "stage_ms_serial": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s / max(calls, 1), 4) for s in sms])),
                 "unit": "ms", "p95": float(np.percentile(lat, 95)), "n_gpus": 1, "steps": len(lat), "higher_is_better": False,
                 "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call"},
                 "check": {"n_tracked": int(res["n_tracked"][0]), "v": res["v"][0].tolist(), "truth": pairs[0][2]["v"].tolist()}}
@@ -310,11 +316,12 @@ def main():
         step_resident()
     barrier()
     l0 = ctx.launch_count()
-    with ClockSampler(local) as clk:
-        ctx.timer_start()
-        for _ in range(args.steps):
-            step_resident()
-        ms = ctx.timer_stop()
+    clk = ClockSampler(local)          # samples until the end-to-end loop ends: every sample is taken under load
+    clk.__enter__()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_resident()
+    ms = ctx.timer_stop()
     launches = ctx.launch_count() - l0
     barrier()
     if dist is not None:
@@ -335,8 +342,8 @@ def main():
     stage_ms, calls = ctx.stage_times()
     ctx.set_profile(False)
     stage_ms = [s / max(calls, 1) for s in stage_ms]
-    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_candidates_kernel", "select_kernel",
-             "lk_track_kernel", "pair_solve_kernel"]
+    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_tile_kernel<false,7>", "select_kernel",
+             "lk_track_fast_kernel", "pair_solve_kernel"]
     P = W * H
     g = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(1, MAX_LEVEL + 1))
     nfeat = float(res["n_features"].mean())
@@ -347,6 +354,15 @@ def main():
            (21 * nfeat + nfeat * nlev * ((WIN[0] + 3) * (WIN[1] + 3) + (WIN[0] + 1) * (WIN[1] + 1))) * B,
            (17 * nfeat + 80) * B]
     dom = int(np.argmax(stage_ms))
+    # DRAM bytes per image of each stage's kernel(s) from the committed ncu --set full capture (profiles/)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = ["pyramid", "eig_nms", "select", "lk", "solve"][dom]
+        if tj.get(key) is not None:
+            traffic = float(tj[key]["dram_bytes_per_pair"]) * B
+    except Exception:
+        pass
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -355,7 +371,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "stage_ms": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s, 4) for s in stage_ms])),
                 "stage_gbs": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"],
                                       [round(a / (s * 1e-3) / 1e9, 2) if s > 0 else None for a, s in zip(alg, stage_ms)])),
@@ -369,6 +385,7 @@ def main():
     for _ in range(args.steps):
         r = ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx)
     e2e_s = time.perf_counter() - t0
+    clk.__exit__()
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
