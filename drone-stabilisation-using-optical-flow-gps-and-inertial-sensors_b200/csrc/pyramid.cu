@@ -6,9 +6,10 @@
 // separable [1 4 6 4 1]/16 in both axes, decimate by two, reflect-101 borders, integer
 // (sum + 128) >> 8 -- bit-exact with OpenCV.
 //
-// One CTA produces a 64x32 tile of the destination level for one image of the batch (blockIdx.z).
-// The 160x67-byte source footprint is staged once in shared memory with 128-bit coalesced loads
-// (byte loads with reflect-101 index fix-up on border tiles only). Every thread then produces a 4x2
+// Persistent CTAs walk the 64x32 output tiles of the whole batch. The 160x67-byte source footprint of a tile is
+// staged in shared memory by the TMA engine (cp.async.bulk, one copy per row, completion on an mbarrier) into
+// one of two stages, so the copy of the next tile overlaps the filtering of the current one (border tiles: 128-bit
+// loads plus a reflect-101 byte gather for the groups that cross the image edge). Every thread then produces a 4x2
 // block of outputs: the horizontal 5-tap filter of four adjacent outputs is eight dp4a on re-aligned
 // words (funnel shifts) per source row, seven source rows feed both output rows, and each output row is
 // written with one 32-bit store. Source bytes are read from HBM exactly once per level (plus halo):
@@ -38,81 +39,156 @@ __device__ __forceinline__ int refl101_bf(int p, int len)
     return max(0, min(p, len - 1));
 }
 
+// ---- TMA (bulk-copy) + mbarrier helpers: raw PTX, sm_90+/sm_100a ---------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one row of a tile: global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_row_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Stage the source footprint of tile (X0,Y0) into `tile`: interior tiles by the TMA engine (one bulk copy per
+// row, completion on `bar`), border tiles by a reflect-101 gather. Returns true when the copy is asynchronous.
+__device__ __forceinline__ bool pyr_stage_tile(const uint8_t* __restrict__ s, int sw, int sh, int spitch, int X0, int Y0,
+                                               uint8_t* tile, unsigned long long* bar, bool aligned, bool tiny)
+{
+    const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;   // source coordinate of tile[0][0]
+    const bool interior = aligned && sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh;
+    if (interior) {
+        if (threadIdx.x == 0) mbar_expect_tx(bar, PS_H * PS_W);
+        __syncwarp();
+        if (threadIdx.x < 96) {      // 3 warps issue the 67 row copies
+            const int r = threadIdx.x;
+            if (r < PS_H) tma_row_g2s(tile + r * PS_PITCH, s + (size_t)(sy0 + r) * spitch + sx0, PS_W, bar);
+        }
+        return true;
+    }
+    // 16-byte groups: a group inside its (reflected) source row is one 128-bit load; only groups that cross
+    // the image edge gather bytes (independent loads: a border tile costs one memory latency, not one per byte)
+    uint4* t128 = (uint4*)tile;
+    constexpr int GPR = PS_W / 16;
+    for (int i = threadIdx.x; i < PS_H * GPR; i += 256) {
+        const int r = i / GPR, c = i - r * GPR;
+        const int yy = tiny ? refl101(sy0 + r, sh) : refl101_bf(sy0 + r, sh);
+        const int gx0 = sx0 + 16 * c;
+        const uint8_t* row = s + (size_t)yy * spitch;
+        uint4 v;
+        if (aligned && gx0 >= 0 && gx0 + 16 <= sw) {
+            v = __ldg((const uint4*)(row + gx0));
+        } else {
+            unsigned int wv[4] = {0, 0, 0, 0};
+            if (tiny) {
+                for (int j = 0; j < 16; ++j) wv[j >> 2] |= (unsigned int)__ldg(row + refl101(gx0 + j, sw)) << (8 * (j & 3));
+            } else {
+                unsigned int bv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bv[j] = __ldg(row + refl101_bf(gx0 + j, sw));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) wv[j >> 2] |= bv[j] << (8 * (j & 3));
+            }
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        t128[r * (PS_PITCH / 16) + c] = v;
+    }
+    return false;
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with two shared-
+// memory stages: the TMA copy of tile i+1 is in flight while tile i is filtered.
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride,
-                uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride)
+                uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride, int tiles_x, int tiles_y, int n_tiles)
 {
-    __shared__ __align__(16) uint8_t tile[PS_H * PS_PITCH];
-    const uint8_t* s = src + (size_t)blockIdx.z * sstride;
-    uint8_t* d = dst + (size_t)blockIdx.z * dstride;
-    const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
-    const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;   // source coordinate of tile[0][0]
-    // Staging in 16-byte groups: a group that lies inside its (reflected) source row is one 128-bit load;
-    // only groups that cross the image edge gather 16 bytes with reflect-101 (independent loads, so a
-    // border tile costs one memory latency, not one per byte).
-    const bool aligned = ((spitch & 15) == 0) && ((((size_t)s) & 15) == 0);
+    __shared__ __align__(128) uint8_t tiles[2][PS_H * PS_PITCH];
+    __shared__ __align__(8) unsigned long long bars[2];
+    const bool aligned = ((spitch & 15) == 0) && ((((size_t)src) & 15) == 0) && ((sstride & 15) == 0);
     const bool tiny = sw < 4 || sh < 4;
-    {
-        uint4* t128 = (uint4*)tile;
-        constexpr int GPR = PS_W / 16;                 // groups per row
-        for (int i = threadIdx.x; i < PS_H * GPR; i += 256) {
-            const int r = i / GPR, c = i - r * GPR;
-            const int yy = tiny ? refl101(sy0 + r, sh) : refl101_bf(sy0 + r, sh);
-            const int gx0 = sx0 + 16 * c;
-            const uint8_t* row = s + (size_t)yy * spitch;
-            uint4 v;
-            if (aligned && gx0 >= 0 && gx0 + 16 <= sw) {
-                v = __ldg((const uint4*)(row + gx0));
-            } else {
-                unsigned int wv[4] = {0, 0, 0, 0};
-                if (tiny) {
-                    for (int j = 0; j < 16; ++j) wv[j >> 2] |= (unsigned int)__ldg(row + refl101(gx0 + j, sw)) << (8 * (j & 3));
-                } else {
-                    unsigned int bv[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) bv[j] = __ldg(row + refl101_bf(gx0 + j, sw));
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) wv[j >> 2] |= bv[j] << (8 * (j & 3));
-                }
-                v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            }
-            t128[r * (PS_PITCH / 16) + c] = v;
-        }
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x2 outputs each
-    const int ox = X0 + 4 * tx, oy = Y0 + 2 * ty;
-    if (ox >= dw || oy >= dh) return;
-    // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
-    // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
-    // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
-    const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
-    unsigned int hsum[7][4];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        const uint32_t* row = t32 + r * (PS_PITCH / 4);
-        unsigned int w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-        unsigned int f01 = __funnelshift_r(w0, w1, 16), f12 = __funnelshift_r(w1, w2, 16), f23 = __funnelshift_r(w2, w3, 16);
-        hsum[r][0] = __dp4a(f12, 0x00000001u, __dp4a(f01, 0x04060401u, 0u));
-        hsum[r][1] = __dp4a(w2, 0x00000001u, __dp4a(w1, 0x04060401u, 0u));
-        hsum[r][2] = __dp4a(f23, 0x00000001u, __dp4a(f12, 0x04060401u, 0u));
-        hsum[r][3] = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x04060401u, 0u));
+    const int per_img = tiles_x * tiles_y;
+    unsigned int phase[2] = {0, 0};
+    bool async_[2] = {false, false};
+    int t = blockIdx.x;
+    if (t >= n_tiles) return;
+    {
+        const int img = t / per_img, rem = t - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
+        async_[0] = pyr_stage_tile(src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[0], &bars[0], aligned, tiny);
     }
-    const bool vec_ok = ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0);
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        if (oy + rr >= dh) break;
-        unsigned int packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            unsigned int v = hsum[2 * rr][k] + hsum[2 * rr + 4][k] + 4u * (hsum[2 * rr + 1][k] + hsum[2 * rr + 3][k]) +
-                             6u * hsum[2 * rr + 2][k];
-            packed |= ((v + 128u) >> 8) << (8 * k);
+    for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int tn = t + gridDim.x;
+        if (tn < n_tiles) {          // prefetch the next tile into the other stage (free since the barrier at loop end)
+            const int img = tn / per_img, rem = tn - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
+            async_[st ^ 1] = pyr_stage_tile(src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[st ^ 1],
+                                            &bars[st ^ 1], aligned, tiny);
         }
-        uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
-        if (vec_ok) *(uint32_t*)drow = packed;
-        else
-            for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
+        if (async_[st]) { mbar_wait(&bars[st], phase[st]); phase[st] ^= 1; }
+        else __syncthreads();        // gathered tile: make the generic-proxy stores visible
+        const int img = t / per_img, rem = t - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
+        const int X0 = tx_ * PT_W, Y0 = ty_ * PT_H;
+        uint8_t* d = dst + (size_t)img * dstride;
+        const uint8_t* tile = tiles[st];
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x2 outputs each
+        const int ox = X0 + 4 * tx, oy = Y0 + 2 * ty;
+        if (ox < dw && oy < dh) {
+            // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
+            // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
+            // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
+            const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
+            unsigned int hsum[7][4];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const uint32_t* row = t32 + r * (PS_PITCH / 4);
+                unsigned int w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+                unsigned int f01 = __funnelshift_r(w0, w1, 16), f12 = __funnelshift_r(w1, w2, 16), f23 = __funnelshift_r(w2, w3, 16);
+                hsum[r][0] = __dp4a(f12, 0x00000001u, __dp4a(f01, 0x04060401u, 0u));
+                hsum[r][1] = __dp4a(w2, 0x00000001u, __dp4a(w1, 0x04060401u, 0u));
+                hsum[r][2] = __dp4a(f23, 0x00000001u, __dp4a(f12, 0x04060401u, 0u));
+                hsum[r][3] = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x04060401u, 0u));
+            }
+            const bool vec_ok = ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (oy + rr >= dh) break;
+                unsigned int packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned int v = hsum[2 * rr][k] + hsum[2 * rr + 4][k] + 4u * (hsum[2 * rr + 1][k] + hsum[2 * rr + 3][k]) +
+                                     6u * hsum[2 * rr + 2][k];
+                    packed |= ((v + 128u) >> 8) << (8 * k);
+                }
+                uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
+                if (vec_ok) *(uint32_t*)drow = packed;
+                else
+                    for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
+            }
+        }
+        fence_proxy_async();         // this stage is refilled by the async proxy two tiles from now
+        __syncthreads();
     }
 }
 
@@ -135,10 +211,16 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         const uint8_t* s; int sp; size_t ss;
         if (l == 1) { s = p->level0; sp = p->level0_pitch; ss = p->level0_stride; }
         else { s = p->base + p->level_off[l - 1]; sp = p->pitch[l - 1]; ss = p->image_stride[l - 1]; }
-        dim3 grid(ofb_div_up(p->w[l], PT_W), ofb_div_up(p->h[l], PT_H), p->n_active);
-        pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss,
-                                                       p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
-                                                       p->image_stride[l]);
+        const int tiles_x = ofb_div_up(p->w[l], PT_W), tiles_y = ofb_div_up(p->h[l], PT_H);
+        const long long n_tiles = (long long)tiles_x * tiles_y * p->n_active;
+        OFB_REQUIRE(n_tiles < (1ll << 31), "pyramid: batch too large");
+        // persistent CTAs: 5 per SM are resident (48 registers x 256 threads, 21.5 KB of shared memory each);
+        // fewer tiles -> one CTA per tile
+        long long grid = (long long)ctx->sm_count * 5;
+        if (grid > n_tiles) grid = n_tiles;
+        pyr_down_kernel<<<(unsigned int)grid, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss,
+                                                                    p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
+                                                                    p->image_stride[l], tiles_x, tiles_y, (int)n_tiles);
         OFB_LAUNCH_CHECK(ctx);
     }
     return OFB_OK;
