@@ -7,7 +7,7 @@
 // (sum + 128) >> 8 -- bit-exact with OpenCV.
 //
 // Persistent CTAs walk the 64x32 output tiles of the whole batch. The 160x67-byte source footprint of a tile is
-// staged in shared memory by the TMA engine (cp.async.bulk, one copy per row, completion on an mbarrier) into
+// staged in shared memory by the TMA engine (cp.async.bulk.tensor through a 3-D tensor map {x, y, image}, completion on an mbarrier) into
 // one of two stages, so the copy of the next tile overlaps the filtering of the current one (border tiles: 128-bit
 // loads plus a reflect-101 byte gather for the groups that cross the image edge). Every thread then produces a 4x2
 // block of outputs: the horizontal 5-tap filter of four adjacent outputs is eight dp4a on re-aligned
@@ -15,6 +15,8 @@
 // written with one 32-bit store. Source bytes are read from HBM exactly once per level (plus halo):
 // algorithmic bytes per level = w*h read + ((w+1)/2)*((h+1)/2) written.
 #include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace {
 
@@ -59,28 +61,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// one row of a tile: global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_row_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar)
+// one tile (PS_W x PS_H bytes of image z at (x,y)) : global -> shared through the tensor map, completion
+// counted in bytes on the mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Stage the source footprint of tile (X0,Y0) into `tile`: interior tiles by the TMA engine (one bulk copy per
 // row, completion on `bar`), border tiles by a reflect-101 gather. Returns true when the copy is asynchronous.
-__device__ __forceinline__ bool pyr_stage_tile(const uint8_t* __restrict__ s, int sw, int sh, int spitch, int X0, int Y0,
-                                               uint8_t* tile, unsigned long long* bar, bool aligned, bool tiny)
+__device__ __forceinline__ bool pyr_stage_tile(const CUtensorMap* tmap, bool use_tma, int img, const uint8_t* __restrict__ s,
+                                               int sw, int sh, int spitch, int X0, int Y0, uint8_t* tile,
+                                               unsigned long long* bar, bool aligned, bool tiny)
 {
     const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;   // source coordinate of tile[0][0]
-    const bool interior = aligned && sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh;
+    const bool interior = use_tma && sx0 >= 0 && sx0 + PS_W <= sw && sy0 >= 0 && sy0 + PS_H <= sh;
     if (interior) {
-        if (threadIdx.x == 0) mbar_expect_tx(bar, PS_H * PS_W);
-        __syncwarp();
-        if (threadIdx.x < 96) {      // 3 warps issue the 67 row copies
-            const int r = threadIdx.x;
-            if (r < PS_H) tma_row_g2s(tile + r * PS_PITCH, s + (size_t)(sy0 + r) * spitch + sx0, PS_W, bar);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, PS_H * PS_W);
+            tma_tile_g2s(tile, tmap, sx0, sy0, img, bar);
         }
         return true;
     }
@@ -117,10 +119,12 @@ __device__ __forceinline__ bool pyr_stage_tile(const uint8_t* __restrict__ s, in
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with two shared-
 // memory stages: the TMA copy of tile i+1 is in flight while tile i is filtered.
 __global__ void __launch_bounds__(256)
-pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride,
-                uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride, int tiles_x, int tiles_y, int n_tiles)
+pyr_down_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                size_t sstride, uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride, int tiles_x, int tiles_y,
+                int n_tiles)
 {
-    __shared__ __align__(128) uint8_t tiles[2][PS_H * PS_PITCH];
+    constexpr int STAGE_BYTES = (PS_H * PS_PITCH + 127) & ~127;    // TMA destinations must be 128-byte aligned
+    __shared__ __align__(128) uint8_t tiles[2][STAGE_BYTES];
     __shared__ __align__(8) unsigned long long bars[2];
     const bool aligned = ((spitch & 15) == 0) && ((((size_t)src) & 15) == 0) && ((sstride & 15) == 0);
     const bool tiny = sw < 4 || sh < 4;
@@ -136,15 +140,16 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, siz
     if (t >= n_tiles) return;
     {
         const int img = t / per_img, rem = t - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
-        async_[0] = pyr_stage_tile(src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[0], &bars[0], aligned, tiny);
+        async_[0] = pyr_stage_tile(&tmap, use_tma != 0, img, src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[0],
+                                   &bars[0], aligned, tiny);
     }
     for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
         const int st = it & 1;
         const int tn = t + gridDim.x;
         if (tn < n_tiles) {          // prefetch the next tile into the other stage (free since the barrier at loop end)
             const int img = tn / per_img, rem = tn - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
-            async_[st ^ 1] = pyr_stage_tile(src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[st ^ 1],
-                                            &bars[st ^ 1], aligned, tiny);
+            async_[st ^ 1] = pyr_stage_tile(&tmap, use_tma != 0, img, src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W,
+                                            ty_ * PT_H, tiles[st ^ 1], &bars[st ^ 1], aligned, tiny);
         }
         if (async_[st]) { mbar_wait(&bars[st], phase[st]); phase[st] ^= 1; }
         else __syncthreads();        // gathered tile: make the generic-proxy stores visible
@@ -205,6 +210,26 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* off = getenv("OFB_NO_TMA");
+        if (!(off && off[0] == '1')) {
+            void* f = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                fn = (PFN_cuTensorMapEncodeTiled)f;
+            else cudaGetLastError();
+        }
+    }
+    return fn;
+}
+
 int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
 {
     for (int l = 1; l < p->n_levels; ++l) {
@@ -218,7 +243,23 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         // fewer tiles -> one CTA per tile
         long long grid = (long long)ctx->sm_count * 5;
         if (grid > n_tiles) grid = n_tiles;
-        pyr_down_kernel<<<(unsigned int)grid, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss,
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        int use_tma = 0;
+        if (PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder()) {
+            // source level as a 3-D u8 tensor {x, y, image}; strides must be multiples of 16 bytes
+            if ((((size_t)s) & 15) == 0 && (sp & 15) == 0 && (ss & 15) == 0 && p->w[l - 1] >= PS_W && p->h[l - 1] >= PS_H) {
+                cuuint64_t gdim[3] = {(cuuint64_t)p->w[l - 1], (cuuint64_t)p->h[l - 1], (cuuint64_t)p->n_active};
+                cuuint64_t gstr[2] = {(cuuint64_t)sp, (cuuint64_t)(p->n_active > 1 ? ss : (size_t)sp * p->h[l - 1])};
+                if (gstr[1] < gstr[0] * gdim[1]) gstr[1] = gstr[0] * gdim[1];
+                cuuint32_t box[3] = {(cuuint32_t)PS_W, (cuuint32_t)PS_H, 1};
+                cuuint32_t estr[3] = {1, 1, 1};
+                CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)s, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
+            }
+        }
+        pyr_down_kernel<<<(unsigned int)grid, 256, 0, ctx->stream>>>(tmap, use_tma, s, p->w[l - 1], p->h[l - 1], sp, ss,
                                                                     p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
                                                                     p->image_stride[l], tiles_x, tiles_y, (int)n_tiles);
         OFB_LAUNCH_CHECK(ctx);
