@@ -241,8 +241,10 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         OFB_REQUIRE(n_tiles < (1ll << 31), "pyramid: batch too large");
         // persistent CTAs: 5 per SM are resident (48 registers x 256 threads, 21.5 KB of shared memory each);
         // fewer tiles -> one CTA per tile
+        // (the in-CTA double buffering pays once a CTA owns several tiles; a level with fewer than ~4 tiles per
+        // resident CTA runs one tile per CTA and relies on the 5 co-resident CTAs to overlap copy and filter)
         long long grid = (long long)ctx->sm_count * 5;
-        if (grid > n_tiles) grid = n_tiles;
+        if (n_tiles < grid * 4) grid = n_tiles;
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         int use_tma = 0;
