@@ -248,7 +248,10 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         int use_tma = 0;
-        if (PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder()) {
+        // TMA staging only where a CTA streams several tiles (its latency is hidden by the two stages); the small
+        // upper levels are latency-bound one-tile-per-CTA launches, where direct 128-bit loads start sooner
+        PFN_cuTensorMapEncodeTiled enc = grid < n_tiles ? tensor_map_encoder() : nullptr;
+        if (enc) {
             // source level as a 3-D u8 tensor {x, y, image}; strides must be multiples of 16 bytes
             if ((((size_t)s) & 15) == 0 && (sp & 15) == 0 && (ss & 15) == 0 && p->w[l - 1] >= PS_W && p->h[l - 1] >= PS_H) {
                 cuuint64_t gdim[3] = {(cuuint64_t)p->w[l - 1], (cuuint64_t)p->h[l - 1], (cuuint64_t)p->n_active};
