@@ -116,6 +116,63 @@ __device__ __forceinline__ bool pyr_stage_tile(const CUtensorMap* tmap, bool use
     return false;
 }
 
+// Filters one staged tile: every thread produces a 4x2 block of outputs.
+__device__ __forceinline__ void pyr_filter_tile(const uint8_t* tile, uint8_t* __restrict__ d, int X0, int Y0, int dw, int dh,
+                                                int dpitch)
+{
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x2 outputs each
+    const int ox = X0 + 4 * tx, oy = Y0 + 2 * ty;
+    if (ox < dw && oy < dh) {
+        // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
+        // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
+        // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
+        const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
+        unsigned int hsum[7][4];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint32_t* row = t32 + r * (PS_PITCH / 4);
+            unsigned int w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+            unsigned int f01 = __funnelshift_r(w0, w1, 16), f12 = __funnelshift_r(w1, w2, 16), f23 = __funnelshift_r(w2, w3, 16);
+            hsum[r][0] = __dp4a(f12, 0x00000001u, __dp4a(f01, 0x04060401u, 0u));
+            hsum[r][1] = __dp4a(w2, 0x00000001u, __dp4a(w1, 0x04060401u, 0u));
+            hsum[r][2] = __dp4a(f23, 0x00000001u, __dp4a(f12, 0x04060401u, 0u));
+            hsum[r][3] = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x04060401u, 0u));
+        }
+        const bool vec_ok = ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            if (oy + rr >= dh) break;
+            unsigned int packed = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned int v = hsum[2 * rr][k] + hsum[2 * rr + 4][k] + 4u * (hsum[2 * rr + 1][k] + hsum[2 * rr + 3][k]) +
+                                 6u * hsum[2 * rr + 2][k];
+                packed |= ((v + 128u) >> 8) << (8 * k);
+            }
+            uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
+            if (vec_ok) *(uint32_t*)drow = packed;
+            else
+                for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
+        }
+    }
+}
+
+// One tile per CTA, staged with direct loads (no mbarrier set-up): used for the small upper levels, which are
+// latency-bound launches.
+__global__ void __launch_bounds__(256)
+pyr_down_small_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride, uint8_t* __restrict__ dst,
+                      int dw, int dh, int dpitch, size_t dstride)
+{
+    __shared__ __align__(16) uint8_t tile[PS_H * PS_PITCH];
+    const uint8_t* s = src + (size_t)blockIdx.z * sstride;
+    const bool aligned = ((spitch & 15) == 0) && ((((size_t)s) & 15) == 0);
+    const bool tiny = sw < 4 || sh < 4;
+    const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
+    pyr_stage_tile(nullptr, false, 0, s, sw, sh, spitch, X0, Y0, tile, nullptr, aligned, tiny);
+    __syncthreads();
+    pyr_filter_tile(tile, dst + (size_t)blockIdx.z * dstride, X0, Y0, dw, dh, dpitch);
+}
+
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with two shared-
 // memory stages: the TMA copy of tile i+1 is in flight while tile i is filtered.
 __global__ void __launch_bounds__(256)
@@ -157,41 +214,7 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uin
         const int X0 = tx_ * PT_W, Y0 = ty_ * PT_H;
         uint8_t* d = dst + (size_t)img * dstride;
         const uint8_t* tile = tiles[st];
-        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x2 outputs each
-        const int ox = X0 + 4 * tx, oy = Y0 + 2 * ty;
-        if (ox < dw && oy < dh) {
-            // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
-            // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
-            // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
-            const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
-            unsigned int hsum[7][4];
-#pragma unroll
-            for (int r = 0; r < 7; ++r) {
-                const uint32_t* row = t32 + r * (PS_PITCH / 4);
-                unsigned int w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-                unsigned int f01 = __funnelshift_r(w0, w1, 16), f12 = __funnelshift_r(w1, w2, 16), f23 = __funnelshift_r(w2, w3, 16);
-                hsum[r][0] = __dp4a(f12, 0x00000001u, __dp4a(f01, 0x04060401u, 0u));
-                hsum[r][1] = __dp4a(w2, 0x00000001u, __dp4a(w1, 0x04060401u, 0u));
-                hsum[r][2] = __dp4a(f23, 0x00000001u, __dp4a(f12, 0x04060401u, 0u));
-                hsum[r][3] = __dp4a(w3, 0x00000001u, __dp4a(w2, 0x04060401u, 0u));
-            }
-            const bool vec_ok = ox + 3 < dw && ((dpitch & 3) == 0) && ((((size_t)d) & 3) == 0);
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                if (oy + rr >= dh) break;
-                unsigned int packed = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    unsigned int v = hsum[2 * rr][k] + hsum[2 * rr + 4][k] + 4u * (hsum[2 * rr + 1][k] + hsum[2 * rr + 3][k]) +
-                                     6u * hsum[2 * rr + 2][k];
-                    packed |= ((v + 128u) >> 8) << (8 * k);
-                }
-                uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
-                if (vec_ok) *(uint32_t*)drow = packed;
-                else
-                    for (int k = 0; k < 4 && ox + k < dw; ++k) drow[k] = (uint8_t)(packed >> (8 * k));
-            }
-        }
+        pyr_filter_tile(tile, d, X0, Y0, dw, dh, dpitch);
         fence_proxy_async();         // this stage is refilled by the async proxy two tiles from now
         __syncthreads();
     }
@@ -245,13 +268,18 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
         // resident CTA runs one tile per CTA and relies on the 5 co-resident CTAs to overlap copy and filter)
         long long grid = (long long)ctx->sm_count * 5;
         if (n_tiles < grid * 4) grid = n_tiles;
+        if (grid == n_tiles) {
+            // small level: latency-bound, one tile per CTA with direct loads
+            dim3 g3(tiles_x, tiles_y, p->n_active);
+            pyr_down_small_kernel<<<g3, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss, p->base + p->level_off[l],
+                                                              p->w[l], p->h[l], p->pitch[l], p->image_stride[l]);
+            OFB_LAUNCH_CHECK(ctx);
+            continue;
+        }
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         int use_tma = 0;
-        // TMA staging only where a CTA streams several tiles (its latency is hidden by the two stages); the small
-        // upper levels are latency-bound one-tile-per-CTA launches, where direct 128-bit loads start sooner
-        PFN_cuTensorMapEncodeTiled enc = grid < n_tiles ? tensor_map_encoder() : nullptr;
-        if (enc) {
+        if (PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder()) {
             // source level as a 3-D u8 tensor {x, y, image}; strides must be multiples of 16 bytes
             if ((((size_t)s) & 15) == 0 && (sp & 15) == 0 && (ss & 15) == 0 && p->w[l - 1] >= PS_W && p->h[l - 1] >= PS_H) {
                 cuuint64_t gdim[3] = {(cuuint64_t)p->w[l - 1], (cuuint64_t)p->h[l - 1], (cuuint64_t)p->n_active};
