@@ -72,22 +72,47 @@ def imu_array(ofb200, pairs, batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 2 ms from a
+    thread (nvidia-smi, the recipe's tool, takes ~50 ms per query -- longer than a 10-step timed region; it is the
+    fallback when NVML cannot be loaded)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    sm = float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.rows.append((sm, self.max, mask))
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    c = [x.strip() for x in out.strip().split(",")]
+                    mask = 0
+                    for (bit, _), val in zip(self.REASONS, c[2:6]):
+                        if val.lower().startswith("active"):
+                            mask |= bit
+                    self.rows.append((float(c[0]), float(c[1]), mask))
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.002 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -99,20 +124,15 @@ class ClockSampler:
         self.t.join(6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [r[0] for r in self.rows]
+        reasons = set()
         for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for nme, val in zip(names, r[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            for bit, name in self.REASONS:
+                if r[2] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
@@ -263,6 +283,8 @@ def extra_workload(args):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
