@@ -444,11 +444,23 @@ def main():
             t = torch.tensor([mc_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             mc_ms = float(t.item())
+        # the same job without the analytic bound R (callers that only consume v_obs: every saved sweep but one)
+        reps_nr = []
+        for _ in range(3):
+            ctx.timer_start()
+            sim.run_steps(steps, pos, flow, count, seed=1, trial_begin=begin, ctx=ctx, want_R=False)
+            reps_nr.append(ctx.timer_stop())
+        nr_ms = float(np.median(reps_nr))
+        if dist is not None:
+            t = torch.tensor([nr_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nr_ms = float(t.item())
         mean, std, mR, n = sim.stats_from_sums(sums, steps)
         total = float(n.sum())
         flop = 140 * MC_POINTS + 300
         mc = {"metric": "MC trials/s", "value": total / (mc_ms * 1e-3), "unit": "trials/s", "trials": total,
               "points": MC_POINTS, "steps": len(steps), "axes": list(MC_AXES), "ms": mc_ms, "ms_reps": [round(r, 3) for r in reps], "wall_ms": mc_wall * 1e3,
+              "value_without_R": total / (nr_ms * 1e-3),
               "scaling": "strong", "precision": "fp32 per-point, fp64 solve/statistics",
               "fp32_tflops_alg": total * flop / (mc_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
               "check_mean_v_step0": [round(float(x), 4) for x in mean[0]]}

@@ -56,7 +56,9 @@ __host__ __device__ void mc_load_params(const ofb_mc_step& s, McParams<T>& p)
 }
 
 // One trial of of_simulation (simulation.py:39-64).
-template <class T>
+// WANT_R = false skips the analytic error bound R (simulation.py:56-64) for callers that only consume v_obs
+// (every saved sweep except sim_err_vs_num); R_out is then 0.
+template <class T, bool WANT_R = true>
 OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* __restrict__ sflow,
                                          uint64_t trial, uint2 key, uint32_t step, double v_out[3], double& R_out)
 {
@@ -87,15 +89,17 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
         m0 += q2 * (yy + (T)1); m1 -= q2 * (px * py); m2 -= q2 * px;
         m3 += q2 * (xx + (T)1); m4 -= q2 * py;        m5 += q2 * (xx + yy);
         g0 -= nx * (py * bz - by); g1 -= nx * (bx - px * bz); g2 -= nx * (px * by - py * bx);
-        // analytic error bound, simulation.py:57-63 (xp = true position)
-        T v_e = dh_rel * (P.n[0] * px0 + P.n[1] * py0 + P.n[2]) + (dn0 * px0 + dn1 * py0 + dn2) +
-                (P.n[0] * dpx + P.n[1] * dpy);
-        T e0 = dfx + (dpy * P.w[2]) + (py0 * dw2 - dw1) + dpx;
-        T e1 = dfy + (-dpx * P.w[2]) + (dw0 - px0 * dw2) + dpy;
-        T e2 = (dpx * P.w[1] - dpy * P.w[0]) + (px0 * dw1 - py0 * dw0);
-        T r0 = v_e * P.v[0] + P.h * e0, r1 = v_e * P.v[1] + P.h * e1, r2 = v_e * P.v[2] + P.h * e2;
-        T qx = py0 * r2 - r1, qy = r0 - px0 * r2, qz = px0 * r1 - py0 * r0;
-        accR += qx * qx + qy * qy + qz * qz;
+        if (WANT_R) {
+            // analytic error bound, simulation.py:57-63 (xp = true position)
+            T v_e = dh_rel * (P.n[0] * px0 + P.n[1] * py0 + P.n[2]) + (dn0 * px0 + dn1 * py0 + dn2) +
+                    (P.n[0] * dpx + P.n[1] * dpy);
+            T e0 = dfx + (dpy * P.w[2]) + (py0 * dw2 - dw1) + dpx;
+            T e1 = dfy + (-dpx * P.w[2]) + (dw0 - px0 * dw2) + dpy;
+            T e2 = (dpx * P.w[1] - dpy * P.w[0]) + (px0 * dw1 - py0 * dw0);
+            T r0 = v_e * P.v[0] + P.h * e0, r1 = v_e * P.v[1] + P.h * e1, r2 = v_e * P.v[2] + P.h * e2;
+            T qx = py0 * r2 - r1, qy = r0 - px0 * r2, qz = px0 * r1 - py0 * r0;
+            accR += qx * qx + qy * qy + qz * qz;
+        }
     }
     double M[6] = {(double)m0, (double)m1, (double)m2, (double)m3, (double)m4, (double)m5};
     double g[3] = {(double)g0, (double)g1, (double)g2};
@@ -106,13 +110,15 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
     v_out[0] = v[0] * he - (W1 * T2 - W2 * T1);
     v_out[1] = v[1] * he - (W2 * T0 - W0 * T2);
     v_out[2] = v[2] * he - (W0 * T1 - W1 * T0);
-    double lmin = ofb_min_eig_sym3(M);
-    R_out = sqrt((double)accR / lmin) + P.baseR;
+    if (WANT_R) {
+        double lmin = ofb_min_eig_sym3(M);
+        R_out = sqrt((double)accR / lmin) + P.baseR;
+    } else R_out = 0.0;
 }
 
 // Register budget left to the compiler (128 for fp32): forcing 5 CTAs/SM (96 registers) was measured slower
 // (2.19e9 vs 2.40e9 trials/s) -- the spills cost more than the extra warps gain.
-template <class T>
+template <class T, bool WANT_R>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const double* __restrict__ pos,
                 const double* __restrict__ flow, uint64_t trial_begin, uint64_t trials, uint2 key,
@@ -134,7 +140,7 @@ mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const d
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < trials; k += stride) {
         double v[3], R;
-        mc_trial<T>(P, spos, sflow, trial_begin + k, key, (uint32_t)(step_id_base + step), v, R);
+        mc_trial<T, WANT_R>(P, spos, sflow, trial_begin + k, key, (uint32_t)(step_id_base + step), v, R);
         if (v_dump) {
             double* o = v_dump + ((size_t)step * trials + k) * 3;
             o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
@@ -382,7 +388,7 @@ extern "C" int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps,
     OFB_REQUIRE(ctx && steps && pos && true_flow && sums_out, "mc_sweep: null argument");
     OFB_REQUIRE(n_steps > 0 && n_steps <= 65535, "mc_sweep: n_steps must be in 1..65535");
     OFB_REQUIRE(trials > 0, "mc_sweep: iterations must be a positive number");
-    OFB_REQUIRE(precision == 0 || precision == 1, "mc_sweep: precision must be 0 (fp32) or 1 (fp64)");
+    OFB_REQUIRE(precision >= 0 && precision <= 3, "mc_sweep: precision must be 0 (fp32) or 1 (fp64), +2 to skip R");
     OFB_REQUIRE(!ofb_is_device_ptr(steps), "mc_sweep: steps must be host memory");
     OFB_TRY(validate_steps(steps, n_steps, total_points));
     OFB_CUDA(cudaSetDevice(ctx->device));
@@ -406,14 +412,17 @@ extern "C" int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps,
     OFB_TRY(ofb_stage_out(ctx, SC_OUT2, R_dump, sizeof(double) * (size_t)n_steps * trials, &o[2]));
     uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     dim3 grid(blocks_per_step, n_steps);
-    if (precision == 0)
-        mc_sweep_kernel<float><<<grid, MC_THREADS, 0, ctx->stream>>>((const ofb_mc_step*)dsteps, step_id_base,
-            (const double*)dpos, (const double*)dflow, trial_begin, trials, key, ctx->scratch[SC_MC1].as<double>(),
-            (double*)o[1].dev, (double*)o[2].dev);
-    else
-        mc_sweep_kernel<double><<<grid, MC_THREADS, 0, ctx->stream>>>((const ofb_mc_step*)dsteps, step_id_base,
-            (const double*)dpos, (const double*)dflow, trial_begin, trials, key, ctx->scratch[SC_MC1].as<double>(),
-            (double*)o[1].dev, (double*)o[2].dev);
+#define OFB_MC_LAUNCH(T, WR)                                                                                          \
+    mc_sweep_kernel<T, WR><<<grid, MC_THREADS, 0, ctx->stream>>>((const ofb_mc_step*)dsteps, step_id_base,             \
+        (const double*)dpos, (const double*)dflow, trial_begin, trials, key, ctx->scratch[SC_MC1].as<double>(),        \
+        (double*)o[1].dev, (double*)o[2].dev)
+    switch (precision) {
+        case 0: OFB_MC_LAUNCH(float, true); break;
+        case 1: OFB_MC_LAUNCH(double, true); break;
+        case 2: OFB_MC_LAUNCH(float, false); break;
+        default: OFB_MC_LAUNCH(double, false); break;
+    }
+#undef OFB_MC_LAUNCH
     OFB_LAUNCH_CHECK(ctx);
     mc_finalize_kernel<<<n_steps, 32, 0, ctx->stream>>>(ctx->scratch[SC_MC1].as<double>(), blocks_per_step,
                                                         (ofb_mc_sums*)o[0].dev);

@@ -75,7 +75,8 @@ def _steps_array(steps):
     return arr
 
 
-def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, precision="fp32", dump=False, ctx=None):
+def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, precision="fp32", dump=False, ctx=None,
+              want_R=True):
     """Run `trials` trials of every step on this GPU. Returns the per-step sums (structured array
     _lib.MCSUMS_DTYPE) and, when dump, v_obs (S,trials,3) and R (S,trials)."""
     ctx = ctx or _lib.default_context()
@@ -94,7 +95,7 @@ def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, p
         Rd = np.zeros((len(steps), trials))
     _lib.check(ctx.lib.ofb_mc_sweep(ctx.h, C.cast(arr, C.c_void_p), len(steps), int(step_id_base), _lib.ptr(pos),
                                     _lib.ptr(flow), len(pos), int(trial_begin), trials, int(seed) & (2 ** 64 - 1),
-                                    PRECISIONS[precision], _lib.ptr(sums), _lib.ptr(vd), _lib.ptr(Rd)))
+                                    PRECISIONS[precision] + (0 if want_R else 2), _lib.ptr(sums), _lib.ptr(vd), _lib.ptr(Rd)))
     if dump:
         return sums, vd, Rd
     return sums

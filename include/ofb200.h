@@ -208,7 +208,8 @@ typedef struct {                         /* per step, sums over trials (mergeabl
  * (trial id, draw block, step id + step_id_base) so any sharding of the trial range reproduces
  * the same union. sums_out: n_steps entries (host or device), OVERWRITTEN. Optional dumps (may
  * be NULL; device or host): v_dump (n_steps x trials x 3), R_dump (n_steps x trials).
- * precision: 0 = fp32 per-point arithmetic with fp64 accumulation, 1 = fp64 throughout. */
+ * precision: 0 = fp32 per-point arithmetic with fp64 solve/statistics, 1 = fp64 throughout; +2 skips the
+ * analytic bound R (sum_R = 0) for callers that only consume v_obs. */
 int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps, int step_id_base,
                  const double* pos, const double* true_flow, int total_points,
                  uint64_t trial_begin, uint64_t trials, uint64_t seed, int precision,

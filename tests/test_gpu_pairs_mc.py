@@ -296,3 +296,15 @@ def test_frame_pairs_pipelined_host_path_equals_resident(ctx):
         r1, p1, n1, s1 = ofb200.frame_pairs(a[sl], b[sl], imu[sl], cfg, want_tracks=True, ctx=ctx)
         assert np.array_equal(r1["v"], res["v"][sl]) and np.array_equal(n1, pn[sl]) and np.array_equal(s1, st[sl])
     assert (res["n_tracked"] > 10).all()
+
+
+def test_mc_without_error_bound_gives_identical_velocities(ctx, pos50):
+    import ofb200
+    sim = ofb200.simulation
+    tf = vo.generate_test_data(pos50, V, W, 1.0, N3, T3)
+    step = sim.make_step(V, W, 1.0, N3, T3, 50, 0, **SIG)
+    for prec in ("fp32", "fp64"):
+        s1, v1, R1 = sim.run_steps([step], pos50, tf, 300, seed=4, precision=prec, dump=True, ctx=ctx)
+        s2, v2, R2 = sim.run_steps([step], pos50, tf, 300, seed=4, precision=prec, dump=True, want_R=False, ctx=ctx)
+        assert np.array_equal(v1, v2) and np.all(R2 == 0) and np.all(R1 > 0)
+        assert np.array_equal(s1["sum_dv"], s2["sum_dv"]) and s2["sum_R"][0] == 0
