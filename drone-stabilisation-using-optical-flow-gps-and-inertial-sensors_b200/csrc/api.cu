@@ -56,6 +56,9 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
     OFB_REQUIRE(ctx, "ctx_destroy: null context");
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->twin) { ofb_ctx_destroy(ctx->twin); cudaSetDevice(ctx->device); }
+    if (ctx->ev_twin_fork) cudaEventDestroy(ctx->ev_twin_fork);
+    if (ctx->ev_twin_join) cudaEventDestroy(ctx->ev_twin_join);
     for (ofb_pyr* p : ctx->pyramids) { cudaFree(p->base); delete p; }
     for (int s = 0; s < 2; ++s)
         for (int i = 0; i < 2; ++i) if (ctx->pair_pyr[s][i]) { cudaFree(ctx->pair_pyr[s][i]->base); delete ctx->pair_pyr[s][i]; }

@@ -92,6 +92,9 @@ struct ofb_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_after_eig = false;                 // ofb_features_device records ev_fork after the lambda_min launch
+    // second context (own stream + scratch) that takes every other chunk of a resident ofb_frame_pairs batch
+    ofb_ctx* twin = nullptr;
+    cudaEvent_t ev_twin_fork = nullptr, ev_twin_join = nullptr;
     // optional per-stage CUDA-event timing of ofb_frame_pairs (ofb_ctx_set_profile)
     bool profile = false;
     cudaEvent_t stage_ev[OFB_NSTAGE_EV] = {};

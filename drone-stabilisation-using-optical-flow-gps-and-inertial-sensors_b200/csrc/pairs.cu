@@ -182,6 +182,40 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
         }
         return ofb_finish_out(ctx, o, 4);
     }
+    // Resident frames: the batch is cut into chunks that alternate between this context and a twin context with its own
+    // stream and scratch. The lambda_min kernel (shared-memory heavy, issue bound) of one chunk and the LK kernel
+    // (register heavy, latency bound) of the other are then co-resident on the SMs instead of running back to back.
+    static const int twin_chunks = [] { const char* e = getenv("OFB_TWIN_CHUNKS"); return e ? atoi(e) : 2; }();
+    if (!host_frames && ofb_is_device_ptr(prev) && ofb_is_device_ptr(next) && !ctx->profile && twin_chunks >= 2 &&
+        n_pairs >= twin_chunks) {
+        if (!ctx->twin) {
+            OFB_TRY(ofb_ctx_create(ctx->device, &ctx->twin));
+            OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_twin_fork, cudaEventDisableTiming));
+            OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_twin_join, cudaEventDisableTiming));
+        }
+        ofb_ctx* tw = ctx->twin;
+        // staged inputs (IMU samples, seed points) were enqueued on this context's stream
+        OFB_CUDA(cudaEventRecord(ctx->ev_twin_fork, ctx->stream));
+        OFB_CUDA(cudaStreamWaitEvent(tw->stream, ctx->ev_twin_fork, 0));
+        const int per = (n_pairs + twin_chunks - 1) / twin_chunks;
+        const uint64_t tw0 = tw->launches;
+        int ci = 0;
+        for (int c0 = 0; c0 < n_pairs; c0 += per, ++ci) {
+            const int n = n_pairs - c0 < per ? n_pairs - c0 : per;
+            ofb_ctx* c = (ci & 1) ? tw : ctx;
+            const int slot = (ci >> 1) & 1;
+            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride, n, per,
+                                    cfg->max_level, false));
+            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n, per,
+                                    cfg->max_level, false));
+            OFB_TRY(run_pairs_chunk(c, cfg, c->pair_pyr[slot][0], c->pair_pyr[slot][1], n, c0, (const ofb_imu_sample*)dimu,
+                                    counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
+        }
+        ctx->launches += tw->launches - tw0;
+        OFB_CUDA(cudaEventRecord(ctx->ev_twin_join, tw->stream));
+        OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_twin_join, 0));
+        return ofb_finish_out(ctx, o, 4);
+    }
     // resident frames (or a small batch): one pass over the whole batch
     OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][0], prev, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
     OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][1], next, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));

@@ -210,7 +210,7 @@ lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restric
                     int jv = ((int)s0[0] * w00 + (int)s0[1] * w01 + (int)s1[0] * w10 + (int)s1[1] * w11 + (1 << 8)) >> 9;
                     ie += abs(jv - (int)pat[i]);
                 }
-                errv = (float)warp_sum_ll(ie) * (1.f / (float)(32 * winW * winH));
+                errv = (float)__reduce_add_sync(0xffffffffu, ie) * (1.f / (float)(32 * winW * winH));
             }
         }
     }
@@ -269,14 +269,17 @@ __device__ __forceinline__ int byte_of(unsigned int w0, unsigned int w1, unsigne
     return (int)((w >> (8 * (j & 3))) & 0xffu);
 }
 
-__device__ __forceinline__ float warp_sum_f(float v)
+// Exact warp sum of int32 lane values, returned as the correctly rounded float of the 64-bit total: two REDUX
+// (low 16 bits unsigned, high part signed; neither can overflow over 32 lanes) instead of a 5-level shuffle chain.
+__device__ __forceinline__ float warp_sum_exact_f(int v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const unsigned int lo = __reduce_add_sync(0xffffffffu, (unsigned int)v & 0xffffu);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return fmaf((float)hi, 65536.f, (float)lo);      // both terms exact in fp32, one rounding
 }
 
-// sum over the lane's 8 pixels of f(jv_k) where jv_k is the Q5 interpolated value of J at pixel k
+// For the lane's 8 pixels: diff = J_k - I_k, both Q5 interpolated values. The dp2a chain starts from
+// Cp[k] = 256 - 512*I_k, so ((sum + 256) >> 9) - I_k comes out of the shift directly (512*I_k is a multiple of 512).
 #define LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, BODY)                                     \
     {                                                                                             \
         unsigned int t1_ = __funnelshift_r(T0, T1, 8), t5_ = __funnelshift_r(T1, T2, 8);          \
@@ -285,10 +288,10 @@ __device__ __forceinline__ float warp_sum_f(float v)
         unsigned int uu_[4] = {U0, u1_, U1, u5_};                                                 \
         _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                           \
             int s_ = ((k >> 2) << 1) | (k & 1);       /* k=0,1,2,3,4,5,6,7 -> 0,1,0,1,2,3,2,3 */  \
-            int jv;                                                                               \
-            if ((k & 2) == 0) { jv = dp2a_lo(Wt, tt_[s_], 256); jv = dp2a_lo(Wb, uu_[s_], jv); }  \
-            else { jv = dp2a_hi(Wt, tt_[s_], 256); jv = dp2a_hi(Wb, uu_[s_], jv); }               \
-            jv >>= 9;                                                                             \
+            int diff;                                                                             \
+            if ((k & 2) == 0) { diff = dp2a_lo(Wt, tt_[s_], Cp[k]); diff = dp2a_lo(Wb, uu_[s_], diff); } \
+            else { diff = dp2a_hi(Wt, tt_[s_], Cp[k]); diff = dp2a_hi(Wb, uu_[s_], diff); }       \
+            diff >>= 9;                                                                           \
             BODY                                                                                  \
         }                                                                                         \
     }
@@ -366,7 +369,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
             if (!ifast && !(rowin && (unsigned)(ix + 8 * hh + k) < (unsigned)w)) { gx = 0; gy = 0; }
             D[k] = ((unsigned int)gx & 0xffffu) | ((unsigned int)gy << 16);
         }
-        int Ip[8], Gx[8], Gy[8];
+        int Cp[8], Gx[8], Gy[8];
         int iA11 = 0, iA12 = 0, iA22 = 0;
         {
             int gxa = (int)(short)(D[0] & 0xffffu), gya = (int)D[0] >> 16;
@@ -382,14 +385,14 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                 int gx = (gxa * w00 + gxb * w01 + gxc * w10 + gxd * w11 + (1 << 13)) >> 14;
                 int gy = (gya * w00 + gyb * w01 + gyc * w10 + gyd * w11 + (1 << 13)) >> 14;
                 if (!((vmask >> k) & 1u)) { gx = 0; gy = 0; }
-                Ip[k] = iv; Gx[k] = gx; Gy[k] = gy;
+                Cp[k] = 256 - 512 * iv; Gx[k] = gx; Gy[k] = gy;
                 iA11 += gx * gx; iA12 += gx * gy; iA22 += gy * gy;
                 gxa = gxb; gya = gyb; gxc = gxd; gyc = gyd;
             }
         }
-        const float A11 = (float)warp_sum_ll(iA11) * FLT_SCALE;
-        const float A12 = (float)warp_sum_ll(iA12) * FLT_SCALE;
-        const float A22 = (float)warp_sum_ll(iA22) * FLT_SCALE;
+        const float A11 = warp_sum_exact_f(iA11) * FLT_SCALE;
+        const float A12 = warp_sum_exact_f(iA12) * FLT_SCALE;
+        const float A22 = warp_sum_exact_f(iA22) * FLT_SCALE;
         float D2 = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dd = A11 - A22;
         const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))) /
@@ -415,13 +418,10 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                                U2 = __shfl_down_sync(0xffffffffu, T2, 2);
             int ib1 = 0, ib2 = 0;
             LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
-                int diff = jv - Ip[k];
                 ib1 += diff * Gx[k]; ib2 += diff * Gy[k];
             })
-            // per-lane partial sums are exact int32; the cross-lane sum is a fixed-order fp32 butterfly (OpenCV
-            // accumulates the same integers in fp32 as well): half the shuffles of the exact 64-bit reduction
-            const float b1 = warp_sum_f((float)ib1) * FLT_SCALE;
-            const float b2 = warp_sum_f((float)ib2) * FLT_SCALE;
+            const float b1 = warp_sum_exact_f(ib1) * FLT_SCALE;
+            const float b2 = warp_sum_exact_f(ib2) * FLT_SCALE;
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D2);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D2);
             qx += dx; qy += dy;
@@ -449,9 +449,9 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                                    U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 int ie = 0;
                 LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
-                    if ((vmask >> k) & 1u) ie += abs(jv - Ip[k]);
+                    if ((vmask >> k) & 1u) ie += abs(diff);
                 })
-                errv = (float)warp_sum_ll(ie) * (1.f / (float)(32 * winW * winH));
+                errv = (float)__reduce_add_sync(0xffffffffu, ie) * (1.f / (float)(32 * winW * winH));
             }
         }
     }

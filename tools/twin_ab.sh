@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_vision.py tests/test_gpu_pairs_mc.py tests/test_gpu_fullsize.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -5
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-mc 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['config'])
+"
