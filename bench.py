@@ -255,6 +255,9 @@ def extra_workload(args):
         res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
         lat = np.array(lat)
         ctx.set_profile(True)
+        for _ in range(3):
+            step()
+        ctx.set_profile(True)
         for _ in range(10):
             step()
         sms, calls = ctx.stage_times()
@@ -364,12 +367,15 @@ def main():
 
     # per-stage durations (CUDA events between the kernels of the same call path)
     ctx.set_profile(True)
+    for _ in range(3):                     # the profiled call path sizes its own scratch on first use
+        step_resident()
+    ctx.set_profile(True)                  # resets the accumulated stage times
     for _ in range(args.steps):
         step_resident()
     stage_ms, calls = ctx.stage_times()
     ctx.set_profile(False)
     stage_ms = [s / max(calls, 1) for s in stage_ms]
-    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_tile_kernel<false,7>", "select_kernel",
+    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_march_kernel<false,7>", "select_kernel",
              "lk_track_fast_kernel", "pair_solve_kernel"]
     P = W * H
     g = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(1, MAX_LEVEL + 1))

@@ -230,23 +230,35 @@ def test_lk_live_cv2_1080p(ctx):
 
 
 def test_two_kernel_variants_agree(ctx):
-    """The tile lambda_min kernel and the generic one build the map from the same exact integer sums:
-    bit-identical maps; the register-resident LK kernel and the generic shared-memory one: identical
-    status, positions equal to fp32 rounding (both accumulate the same integers exactly)."""
+    """The marching, the tile and the generic lambda_min kernels build the map from the same exact integer sums:
+    bit-identical maps and feature lists; the register-resident LK kernel and the generic shared-memory one:
+    identical status, positions equal to fp32 rounding (both accumulate the same integers exactly)."""
     import ofb200
-    for (h, w), seed in [((240, 320), 21), ((131, 517), 22), ((480, 640), 23)]:
+
+    def with_env(name, fn):
+        os.environ[name] = "1"
+        try:
+            return fn()
+        finally:
+            os.environ[name] = "0"
+
+    rng = np.random.default_rng(5)
+    for (h, w), seed in [((240, 320), 21), ((131, 517), 22), ((480, 640), 23), ((97, 1003), 24), ((300, 121), 25)]:
         img = synth.texture(h, w, seed)
+        mask = (rng.random((h, w)) > 0.3).astype(np.uint8)
         for bs in (3, 7, 12, 32):
-            fast = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
-            os.environ["OFB_EIG_GENERIC"] = "1"
-            try:
-                gen = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
-                pts_gen = ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx)
-            finally:
-                os.environ["OFB_EIG_GENERIC"] = "0"
+            both = lambda: (ofb200.cornerMinEigenVal(img, bs, ctx=ctx),
+                            ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx),
+                            ofb200.goodFeaturesToTrack(img, 0, 0.05, 3, mask=mask, blockSize=bs, ctx=ctx))
+            fast, pts_fast, ptsm_fast = both()                      # marching kernel for blockSize 3, 7, 12
+            tile, pts_tile, ptsm_tile = with_env("OFB_EIG_TILE", both)
+            gen, pts_gen, ptsm_gen = with_env("OFB_EIG_GENERIC", both)
+            assert np.array_equal(fast, tile), (h, w, bs, np.abs(fast - tile).max(), np.argwhere(fast != tile)[:5])
             assert np.array_equal(fast, gen), (h, w, bs, np.abs(fast - gen).max())
-            pts_fast = ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx)
             assert np.array_equal(as_list(pts_fast), as_list(pts_gen))
+            assert np.array_equal(as_list(pts_fast), as_list(pts_tile))
+            assert np.array_equal(as_list(ptsm_fast), as_list(ptsm_gen))
+            assert np.array_equal(as_list(ptsm_fast), as_list(ptsm_tile))
     for case in range(3):
         a, b = synth.affine_pair(240, 320, 30 + case, shift=(3.5 + case, -2.25), rot=0.01 * case)
         pts = io.good_features(a, 150, 0.01, 8, block_size=7)
