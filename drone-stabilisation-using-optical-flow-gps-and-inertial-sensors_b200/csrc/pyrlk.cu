@@ -242,23 +242,33 @@ __device__ __forceinline__ int dp2a_hi(int w16x2, unsigned int bytes, int c)
     return d;
 }
 
-// 12 bytes of row Y starting at column X0 (bytes j=0..11 <-> columns X0+j) as three words.
-// fast: the 16 bytes from the aligned-down address are inside the row; slow: per-byte reflect-101.
-__device__ __forceinline__ void load12(const uint8_t* __restrict__ img, int w, int h, int pitch, int X0, int Y, bool fast,
+// Column index reflected into [0, len): exact reflect-101 for p in [-len, 2*len) (two folds), which covers every
+// patch position the tracker can reach (|offset| <= window + 9 columns, len > window).
+__device__ __forceinline__ int refl_col(int p, int len)
+{
+    p = p < 0 ? -p : p;
+    p = p >= len ? 2 * len - 2 - p : p;
+    p = p < 0 ? -p : p;
+    return min(p, len - 1);
+}
+
+// 12 bytes of image row Yr (already inside the image) starting at column X0 (bytes j=0..11 <-> columns X0+j) as
+// three words. colfast (warp-uniform): the 16 bytes from the aligned-down address are inside the row -> four
+// 32-bit loads and funnel shifts; else twelve independent byte loads with reflect-101 columns.
+__device__ __forceinline__ void load12(const uint8_t* __restrict__ img, int w, int pitch, int X0, int Yr, bool colfast,
                                        unsigned int& o0, unsigned int& o1, unsigned int& o2)
 {
-    if (fast) {
-        const uint8_t* p = img + (size_t)Y * pitch + X0;
-        unsigned long long a = (unsigned long long)p;
+    const uint8_t* row = img + (size_t)Yr * pitch;
+    if (colfast) {
+        unsigned long long a = (unsigned long long)(row + X0);
         const unsigned int* q = (const unsigned int*)(a & ~3ull);
         unsigned int sh = (unsigned int)(a & 3ull) * 8u;
         unsigned int a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
         o0 = __funnelshift_r(a0, a1, sh); o1 = __funnelshift_r(a1, a2, sh); o2 = __funnelshift_r(a2, a3, sh);
     } else {
-        const uint8_t* row = img + (size_t)refl101(Y, h) * pitch;
         unsigned int v[3] = {0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 12; ++j) v[j >> 2] |= (unsigned int)__ldg(row + refl101(X0 + j, w)) << (8 * (j & 3));
+        for (int j = 0; j < 12; ++j) v[j >> 2] |= (unsigned int)__ldg(row + refl_col(X0 + j, w)) << (8 * (j & 3));
         o0 = v[0]; o1 = v[1]; o2 = v[2];
     }
 }
@@ -346,12 +356,18 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
         bil_weights(a, b, w00, w01, w10, w11);
         // ---- template ---------------------------------------------------------------------------------
         // rows iy+r-1, iy+r, iy+r+1, bytes j=0..11 <-> columns ix+8hh-1+j
-        const bool ifast = ix - 1 >= ilow && ix + 8 + 15 <= w && iy - 1 >= 0 && iy + 16 < h;
+        // warp-uniform: all columns / all rows of the patch (plus the Scharr ring) inside the image
+        const bool icol = ix - 1 >= ilow && ix + 8 + 15 <= w, irow = iy - 1 >= 0 && iy + 16 < h;
+        const bool ifast = icol && irow;
         const int X0 = ix - 1 + 8 * hh;
         unsigned int A0, A1, A2, B0, B1, B2, C0, C1, C2;
-        load12(I, w, h, ipitch, X0, iy + r - 1, ifast, A0, A1, A2);
-        load12(I, w, h, ipitch, X0, iy + r, ifast, B0, B1, B2);
-        load12(I, w, h, ipitch, X0, iy + r + 1, ifast, C0, C1, C2);
+        {
+            int ya = iy + r - 1, yb = iy + r, yc = iy + r + 1;
+            if (!irow) { ya = refl101(ya, h); yb = refl101(yb, h); yc = refl101(yc, h); }
+            load12(I, w, ipitch, X0, ya, icol, A0, A1, A2);
+            load12(I, w, ipitch, X0, yb, icol, B0, B1, B2);
+            load12(I, w, ipitch, X0, yc, icol, C0, C1, C2);
+        }
         int t0[11], t1[11];
 #pragma unroll
         for (int j = 0; j < 11; ++j) {
@@ -366,8 +382,12 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
         for (int k = 0; k < 9; ++k) {
             int gx = t0[k + 2] - t0[k];
             int gy = 3 * (t1[k] + t1[k + 2]) + 10 * t1[k + 1];
-            if (!ifast && !(rowin && (unsigned)(ix + 8 * hh + k) < (unsigned)w)) { gx = 0; gy = 0; }
             D[k] = ((unsigned int)gx & 0xffffu) | ((unsigned int)gy << 16);
+        }
+        if (!ifast) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (!(rowin && (unsigned)(ix + 8 * hh + k) < (unsigned)w)) D[k] = 0u;
         }
         int Cp[8], Gx[8], Gy[8];
         int iA11 = 0, iA12 = 0, iA22 = 0;
@@ -411,9 +431,9 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
             a = qx - (float)jx; b = qy - (float)jy;
             bil_weights(a, b, w00, w01, w10, w11);
             const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
-            const bool jfast = jx >= jlow && jx + 8 + 16 <= w && jy >= 0 && jy + 15 < h;
+            const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
             unsigned int T0, T1, T2;
-            load12(J, w, h, jpitch, jx + 8 * hh, jy + r, jfast, T0, T1, T2);
+            load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
             const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
                                U2 = __shfl_down_sync(0xffffffffu, T2, 2);
             int ib1 = 0, ib2 = 0;
@@ -442,9 +462,9 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                 a = rx - (float)jx; b = ry - (float)jy;
                 bil_weights(a, b, w00, w01, w10, w11);
                 const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
-                const bool jfast = jx >= jlow && jx + 8 + 16 <= w && jy >= 0 && jy + 15 < h;
+                const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
                 unsigned int T0, T1, T2;
-                load12(J, w, h, jpitch, jx + 8 * hh, jy + r, jfast, T0, T1, T2);
+                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
                 const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
                                    U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 int ie = 0;

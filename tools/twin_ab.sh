@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_pairs_mc.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -5
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-mc 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
@@ -7,4 +7,3 @@ for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['stage_ms'])
 "
-OFB_TWIN_CHUNKS=0 timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct -k regex:eig_march --clock-control none -c 2 python tools/profile_pairs.py --batch 32 --steps 1 --mc-trials 1000 2>/dev/null | grep -E "duration|inst_executed|issue_active"
