@@ -17,6 +17,7 @@
 // full-frame Scharr images per level; here gradients are formed only under the windows, so the
 // derivative images (the largest share of OpenCV's LK time) never exist.
 // The kernel is latency/issue bound (dependent iterations), not HBM bound: DESIGN.md, "LK".
+#include <climits>
 #include "common.cuh"
 #include "pyrlk.cuh"
 
@@ -425,17 +426,23 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
         float qx = nx - hwx, qy = ny - hwy;
         float pdx = 0.f, pdy = 0.f;
         bool lost = false;
+        unsigned int T0 = 0, T1 = 0, T2 = 0, U0 = 0, U1 = 0, U2 = 0;
+        int cjx = INT_MIN, cjy = INT_MIN;
         for (int j = 0; j < P.max_count; ++j) {
             const int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
             if (jx < -winW || jx >= w || jy < -winH || jy >= h) { lost = true; break; }
             a = qx - (float)jx; b = qy - (float)jy;
             bil_weights(a, b, w00, w01, w10, w11);
             const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
-            const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-            unsigned int T0, T1, T2;
-            load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
-            const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
-                               U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+            // the patch rows stay in registers while the integer position does not move (most Newton steps are
+            // sub-pixel): only the bilinear weights change then
+            if (jx != cjx || jy != cjy) {
+                const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
+                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
+                U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                cjx = jx; cjy = jy;
+            }
             int ib1 = 0, ib2 = 0;
             LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
                 ib1 += diff * Gx[k]; ib2 += diff * Gy[k];
@@ -462,11 +469,12 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                 a = rx - (float)jx; b = ry - (float)jy;
                 bil_weights(a, b, w00, w01, w10, w11);
                 const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
-                const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-                unsigned int T0, T1, T2;
-                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
-                const unsigned int U0 = __shfl_down_sync(0xffffffffu, T0, 2), U1 = __shfl_down_sync(0xffffffffu, T1, 2),
-                                   U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                if (jx != cjx || jy != cjy) {
+                    const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
+                    load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                    U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
+                    U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                }
                 int ie = 0;
                 LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
                     if ((vmask >> k) & 1u) ie += abs(diff);
