@@ -100,7 +100,13 @@ __device__ __forceinline__ bool pyr_stage_tile(const CUtensorMap* tmap, bool use
             v = __ldg((const uint4*)(row + gx0));
         } else {
             unsigned int wv[4] = {0, 0, 0, 0};
-            if (tiny) {
+            // the filter never reads tile bytes 0..13 and 145..159 (outputs 4tx+k read bytes 8tx+14+2k .. +4):
+            // the first group needs its last two bytes, the last group its first byte
+            if (c == 0 && !tiny) {
+                wv[3] = ((unsigned int)__ldg(row + refl101_bf(gx0 + 14, sw)) << 16) | ((unsigned int)__ldg(row + refl101_bf(gx0 + 15, sw)) << 24);
+            } else if (c == GPR - 1 && !tiny) {
+                wv[0] = (unsigned int)__ldg(row + refl101_bf(gx0, sw));
+            } else if (tiny) {
                 for (int j = 0; j < 16; ++j) wv[j >> 2] |= (unsigned int)__ldg(row + refl101(gx0 + j, sw)) << (8 * (j & 3));
             } else {
                 unsigned int bv[16];
@@ -195,26 +201,29 @@ pyr_down_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uin
     bool async_[2] = {false, false};
     int t = blockIdx.x;
     if (t >= n_tiles) return;
-    {
-        const int img = t / per_img, rem = t - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
-        async_[0] = pyr_stage_tile(&tmap, use_tma != 0, img, src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[0],
-                                   &bars[0], aligned, tiny);
-    }
-    for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    // tile coordinates advance by gridDim.x tiles per step: one division up front, carries afterwards
+    const int G = gridDim.x;
+    const int d_img = G / per_img, d_rem = G - d_img * per_img, d_ty = d_rem / tiles_x, d_tx = d_rem - d_ty * tiles_x;
+    int img = t / per_img, ty_, tx_;
+    { const int rem = t - img * per_img; ty_ = rem / tiles_x; tx_ = rem - ty_ * tiles_x; }
+    int nimg = img, nty = ty_, ntx = tx_;
+    auto advance = [&](int& im, int& y, int& x) {
+        x += d_tx; if (x >= tiles_x) { x -= tiles_x; ++y; }
+        y += d_ty; if (y >= tiles_y) { y -= tiles_y; ++im; }
+        im += d_img;
+    };
+    async_[0] = pyr_stage_tile(&tmap, use_tma != 0, img, src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W, ty_ * PT_H, tiles[0],
+                               &bars[0], aligned, tiny);
+    for (int it = 0; t < n_tiles; t += G, ++it) {
         const int st = it & 1;
-        const int tn = t + gridDim.x;
-        if (tn < n_tiles) {          // prefetch the next tile into the other stage (free since the barrier at loop end)
-            const int img = tn / per_img, rem = tn - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
-            async_[st ^ 1] = pyr_stage_tile(&tmap, use_tma != 0, img, src + (size_t)img * sstride, sw, sh, spitch, tx_ * PT_W,
-                                            ty_ * PT_H, tiles[st ^ 1], &bars[st ^ 1], aligned, tiny);
-        }
+        advance(nimg, nty, ntx);
+        if (t + G < n_tiles)         // prefetch the next tile into the other stage (free since the barrier at loop end)
+            async_[st ^ 1] = pyr_stage_tile(&tmap, use_tma != 0, nimg, src + (size_t)nimg * sstride, sw, sh, spitch, ntx * PT_W,
+                                            nty * PT_H, tiles[st ^ 1], &bars[st ^ 1], aligned, tiny);
         if (async_[st]) { mbar_wait(&bars[st], phase[st]); phase[st] ^= 1; }
         else __syncthreads();        // gathered tile: make the generic-proxy stores visible
-        const int img = t / per_img, rem = t - img * per_img, ty_ = rem / tiles_x, tx_ = rem - ty_ * tiles_x;
-        const int X0 = tx_ * PT_W, Y0 = ty_ * PT_H;
-        uint8_t* d = dst + (size_t)img * dstride;
-        const uint8_t* tile = tiles[st];
-        pyr_filter_tile(tile, d, X0, Y0, dw, dh, dpitch);
+        pyr_filter_tile(tiles[st], dst + (size_t)img * dstride, tx_ * PT_W, ty_ * PT_H, dw, dh, dpitch);
+        img = nimg; ty_ = nty; tx_ = ntx;
         fence_proxy_async();         // this stage is refilled by the async proxy two tiles from now
         __syncthreads();
     }

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_pairs_mc.py -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -5
+timeout 900 python -m pytest tests -m gpu -q -x --tb=short -p no:cacheprovider 2>&1 | tail -5
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-mc 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
