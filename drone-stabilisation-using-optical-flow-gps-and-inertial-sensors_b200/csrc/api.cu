@@ -69,7 +69,9 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux2_stream) cudaStreamDestroy(ctx->aux2_stream);
     for (int i = 0; i < OFB_NSCRATCH; ++i) ctx->scratch[i].release();
     for (int i = 0; i < 4; ++i) ctx->pin[i].release();
     for (int i = 0; i < OFB_NSTAGE_EV; ++i) if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);

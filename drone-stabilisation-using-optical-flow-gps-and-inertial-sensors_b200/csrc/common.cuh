@@ -89,8 +89,8 @@ struct ofb_ctx {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // the ordered-selection kernel occupies one CTA per image; the pyramid kernels of the same batch run beside
     // it on aux_stream (fork after the lambda_min kernel, join before LK)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     bool fork_after_eig = false;                 // ofb_features_device records ev_fork after the lambda_min launch
     // second context (own stream + scratch) that takes every other chunk of a resident ofb_frame_pairs batch
     ofb_ctx* twin = nullptr;

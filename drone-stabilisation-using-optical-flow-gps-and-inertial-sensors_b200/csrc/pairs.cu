@@ -59,8 +59,10 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
     const bool overlap = cfg->detect && !mark;
     if (overlap && !ctx->aux_stream) {
         OFB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        OFB_CUDA(cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));
         OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
     }
     STAGE_MARK(0);
     if (!overlap) {
@@ -82,16 +84,21 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
         OFB_TRY(fr);
         counts = &st->n_out; counts_stride = (int)(sizeof(FeatImageState) / sizeof(int));
         if (overlap) {
-            // aux_stream: wait for the lambda_min kernel, build both pyramids beside the selection kernel
+            // aux streams: wait for the lambda_min kernel, build the two pyramids beside the selection kernel (one
+            // stream each: the small upper levels are latency-bound launches and overlap)
             OFB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            OFB_CUDA(cudaStreamWaitEvent(ctx->aux2_stream, ctx->ev_fork, 0));
             cudaStream_t main_stream = ctx->stream;
             ctx->stream = ctx->aux_stream;
             int pr = ofb_pyr_build_device(ctx, pp);
+            ctx->stream = ctx->aux2_stream;
             if (pr == OFB_OK) pr = ofb_pyr_build_device(ctx, pn);
             ctx->stream = main_stream;
             OFB_TRY(pr);
             OFB_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            OFB_CUDA(cudaEventRecord(ctx->ev_join2, ctx->aux2_stream));
             OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
         }
     } else {
         if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[2], ctx->stream));
