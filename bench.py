@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frame pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs generated (tiled to the batch)")
     ap.add_argument("--mc-trials", type=int, default=MC_TOTAL)
     ap.add_argument("--no-mc", action="store_true")
@@ -323,12 +323,33 @@ def main():
     ctx.memcpy(d_next, h_next, h_next.nbytes)
     d_imu = torch.from_numpy(imu.view(np.uint8).reshape(-1).copy()).cuda()
     d_res = torch.zeros(B * ofb200._lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    # "single stream" (BASELINE config 2): B+1 consecutive frames, pair k = (frame k, frame k+1). The synthetic stream
+    # alternates the base view with a moved view (even pairs: motion k/2 forward, odd pairs: the way back), so every
+    # consecutive pair is a small, known camera motion.
+    h_seq = ctx.pinned_array((B + 1, H, W), np.uint8)
+    imu_seq = np.zeros(B, ofb200._lib.IMU_DTYPE)
+    for k in range(B + 1):
+        j = (k // 2) % len(pairs)
+        h_seq[k] = pairs[j][0] if k % 2 == 0 else pairs[j][1]
+    for k in range(B):
+        mo = pairs[(k // 2) % len(pairs)][2]
+        imu_seq["d"][k], imu_seq["n"][k] = mo["d"], mo["n"]
+        imu_seq["w"][k] = mo["w"] if k % 2 == 0 else -np.asarray(mo["w"])
+    d_seq = torch.empty((B + 1, H, W), dtype=torch.uint8, device="cuda")
+    ctx.memcpy(d_seq, h_seq, h_seq.nbytes)
+    d_imu_seq = torch.from_numpy(imu_seq.view(np.uint8).reshape(-1).copy()).cuda()
     torch.cuda.synchronize()
     lib, C = ctx.lib, __import__("ctypes")
+    P = W * H
 
-    def step_resident():
+    def step_independent():
         ofb200._lib.check(lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, ofb200._lib.ptr(d_prev), ofb200._lib.ptr(d_next), W,
                                               W * H, ofb200._lib.ptr(d_imu), None, None, ofb200._lib.ptr(d_res), None, None,
+                                              None))
+
+    def step_resident():
+        ofb200._lib.check(lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, d_seq.data_ptr(), d_seq.data_ptr() + P, W,
+                                              W * H, ofb200._lib.ptr(d_imu_seq), None, None, ofb200._lib.ptr(d_res), None, None,
                                               None))
 
     def barrier():
@@ -359,11 +380,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
-    # correctness of what was timed: results must be plausible velocities
+    # correctness of what was timed: results must be plausible velocities (forward pairs have an exact truth)
     res = np.zeros(B, ofb200._lib.RESULT_DTYPE)
     ctx.memcpy(res, d_res, res.nbytes)
-    verr = max(np.abs(res["v"][i] - pairs[i % len(pairs)][2]["v"]).max() for i in range(B))
+    verr = max(np.abs(res["v"][k] - pairs[(k // 2) % len(pairs)][2]["v"]).max() for k in range(0, B, 2))
     tracked = int(res["n_tracked"].min())
+    # the same number of pairs as independent (prev, next) buffers: both frames of every pair uploaded / pyramided
+    for _ in range(args.warmup):
+        step_independent()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_independent()
+    ms_ind = ctx.timer_stop()
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms_ind], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ind = float(t.item())
+    res_i = np.zeros(B, ofb200._lib.RESULT_DTYPE)
+    ctx.memcpy(res_i, d_res, res_i.nbytes)
+    verr_i = max(np.abs(res_i["v"][i] - pairs[i % len(pairs)][2]["v"]).max() for i in range(B))
 
     # per-stage durations (CUDA events between the kernels of the same call path)
     ctx.set_profile(True)
@@ -375,13 +412,12 @@ def main():
     stage_ms, calls = ctx.stage_times()
     ctx.set_profile(False)
     stage_ms = [s / max(calls, 1) for s in stage_ms]
-    names = ["pyramid(pyr_down_kernel x%d levels x2 frames)" % MAX_LEVEL, "eig_march_kernel<false,7>", "select_kernel",
+    names = ["pyramid(pyr_down_kernel x%d levels)" % MAX_LEVEL, "eig_march_kernel<false,7>", "select_kernel",
              "lk_track_fast_kernel", "pair_solve_kernel"]
-    P = W * H
     g = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(1, MAX_LEVEL + 1))
     nfeat = float(res["n_features"].mean())
     nlev = MAX_LEVEL + 1
-    alg = [2 * (P + g) * B,
+    alg = [(P + g) * (B + 1),
            (P + 8 * 4 * nfeat) * B,
            (8 * 4 * nfeat + 8 * nfeat) * B,
            (21 * nfeat + nfeat * nlev * ((WIN[0] + 3) * (WIN[1] + 3) + (WIN[0] + 1) * (WIN[1] + 1))) * B,
@@ -411,20 +447,29 @@ def main():
                 "note": "LK is latency/issue bound (dependent Newton iterations), not HBM bound; see DESIGN.md"}
 
     # end to end through the public API: pinned host frames in, host results out, every step
-    for _ in range(max(1, args.warmup // 2)):
-        ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx)
-    e2e_s = time.perf_counter() - t0
+    def e2e_run(fn):
+        for _ in range(max(1, args.warmup // 2)):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r_ = fn()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t_ = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            dt = float(t_.item())
+        return dt, r_
+
+    e2e_s, r = e2e_run(lambda: ofb200.frame_sequence(h_seq, imu_seq, cfg, ctx=ctx))
+    e2e_i, _ = e2e_run(lambda: ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx))
     clk.__exit__()
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * P + imu.nbytes),
-           "d2h_bytes_per_step": int(r.nbytes)}
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int((B + 1) * P + imu_seq.nbytes),
+           "d2h_bytes_per_step": int(r.nbytes), "h2d_gbs": round((B + 1) * P * args.steps / e2e_s / 1e9, 1)}
+    independent = {"value": world * B * args.steps / (ms_ind * 1e-3), "ms_per_step": ms_ind / args.steps,
+                   "e2e": world * B * args.steps / e2e_i, "h2d_bytes_per_step": int(2 * B * P + imu.nbytes),
+                   "max_abs_v_error_vs_truth": float(verr_i),
+                   "note": "same pairs as separate prev/next buffers (no frame shared between pairs)"}
 
     # Monte-Carlo sweep, trial ranges sharded over the ranks, sums merged with one all-reduce
     mc = None
@@ -486,12 +531,13 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-                "config": {"workload": "C2: 1920x1080 frame pairs, 1000 features, maxLevel 4, detect+track+solve",
-                           "pairs_per_step_per_gpu": B, "distinct_pairs": len(pairs),
-                           "l2": "inputs larger than L2 (%d MB of frames per step)" % (2 * B * P // 2 ** 20),
+                "config": {"workload": "C2: single 1920x1080 stream, consecutive frame pairs, 1000 features, maxLevel 4, "
+                                       "detect+track+solve",
+                           "pairs_per_step_per_gpu": B, "frames_per_step_per_gpu": B + 1, "distinct_motions": len(pairs),
+                           "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
                            "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk.summary(), "mc": mc,
+                "clocks": clk.summary(), "independent_pairs": independent, "mc": mc,
                 "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
         print(json.dumps(line))
     if dist is not None:

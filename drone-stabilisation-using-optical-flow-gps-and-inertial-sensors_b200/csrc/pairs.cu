@@ -48,10 +48,13 @@ pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict_
 }  // namespace
 
 // Stages 1b-4 for pairs [c0, c0+n) whose level-0 frames already sit in pp/pn (images 0..n-1 of each).
+// Sequence layout (pn == pp): pp holds n+1 consecutive frames of one stream, pair i = (image i, image i+1), so every
+// interior frame's pyramid is built once and serves as "next" of one pair and "prev" of the following one.
 static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, ofb_pyr* pn, int n, int c0,
                            const ofb_imu_sample* dimu, const int* counts_in, float* d_prev, float* d_next, uint8_t* d_stat,
                            ofb_pair_result* d_res, bool mark)
 {
+    const bool seq = pn == pp;
     const int w = cfg->width, h = cfg->height, K = cfg->max_corners;
 #define STAGE_MARK(i) do { if (mark) OFB_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream)); } while (0)
     // Detection only needs level 0, and the selection kernel keeps just one SM per image busy: unless stage
@@ -67,7 +70,7 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
     STAGE_MARK(0);
     if (!overlap) {
         OFB_TRY(ofb_pyr_build_device(ctx, pp));
-        OFB_TRY(ofb_pyr_build_device(ctx, pn));
+        if (!seq) OFB_TRY(ofb_pyr_build_device(ctx, pn));
     }
     STAGE_MARK(1);
     float* cp = d_prev + (size_t)c0 * 2 * K;
@@ -92,7 +95,7 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
             ctx->stream = ctx->aux_stream;
             int pr = ofb_pyr_build_device(ctx, pp);
             ctx->stream = ctx->aux2_stream;
-            if (pr == OFB_OK) pr = ofb_pyr_build_device(ctx, pn);
+            if (pr == OFB_OK && !seq) pr = ofb_pyr_build_device(ctx, pn);
             ctx->stream = main_stream;
             OFB_TRY(pr);
             OFB_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
@@ -106,7 +109,7 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
     }
     STAGE_MARK(3);
     OFB_TRY(ctx->scratch[SC_ERR].reserve(sizeof(float) * (size_t)n * K));
-    OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, 0, 1, n, cp, counts, counts_stride, K, (size_t)K, cfg->win_w, cfg->win_h,
+    OFB_TRY(ofb_lk_device(ctx, pp, 0, 1, pn, seq ? 1 : 0, 1, n, cp, counts, counts_stride, K, (size_t)K, cfg->win_w, cfg->win_h,
                           cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, cn, cs, ctx->scratch[SC_ERR].as<float>()));
     STAGE_MARK(4);
     TrackLoader ld{cp, cn, cs, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
@@ -154,7 +157,9 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
             OFB_CUDA(cudaMemcpyAsync(d_prev, pts_in, sizeof(float) * 2 * npts, cudaMemcpyDefault, ctx->stream));
     }
     const bool host_frames = !ofb_is_device_ptr(prev) && !ofb_is_device_ptr(next);
-    const int chunk = 8;
+    // consecutive frames of one stream in one buffer: each frame is uploaded and its pyramid built once per sub-batch
+    const bool seq = next == prev + image_stride && n_pairs > 1;
+    const int chunk = seq ? 16 : 8;
     if (host_frames && n_pairs > chunk && !ctx->profile) {
         // Host frames: pipeline sub-batches. The H2D copy of sub-batch i+1 runs on copy_stream into the other
         // workspace slot while sub-batch i computes on the context stream.
@@ -174,17 +179,17 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
             const int slot = ci & 1;
             OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));
             ctx->upload_stream = ctx->copy_stream;
-            int r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
-                                    chunk, cfg->max_level, false);
-            if (r == OFB_OK)
+            int r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
+                                    seq ? n + 1 : n, seq ? chunk + 1 : chunk, cfg->max_level, false);
+            if (r == OFB_OK && !seq)
                 r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
                                     chunk, cfg->max_level, false);
             ctx->upload_stream = nullptr;
             OFB_TRY(r);
             OFB_CUDA(cudaEventRecord(ctx->ev_ready[slot], ctx->copy_stream));
             OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[slot], 0));
-            OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[slot][0], ctx->pair_pyr[slot][1], n, c0, (const ofb_imu_sample*)dimu,
-                                    counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
+            OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[slot][0], seq ? ctx->pair_pyr[slot][0] : ctx->pair_pyr[slot][1], n, c0,
+                                    (const ofb_imu_sample*)dimu, counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
             OFB_CUDA(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
         }
         return ofb_finish_out(ctx, o, 4);
@@ -211,12 +216,13 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
             const int n = n_pairs - c0 < per ? n_pairs - c0 : per;
             ofb_ctx* c = (ci & 1) ? tw : ctx;
             const int slot = (ci >> 1) & 1;
-            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride, n, per,
-                                    cfg->max_level, false));
-            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n, per,
-                                    cfg->max_level, false));
-            OFB_TRY(run_pairs_chunk(c, cfg, c->pair_pyr[slot][0], c->pair_pyr[slot][1], n, c0, (const ofb_imu_sample*)dimu,
-                                    counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
+            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
+                                    seq ? n + 1 : n, seq ? per + 1 : per, cfg->max_level, false));
+            if (!seq)
+                OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n, per,
+                                        cfg->max_level, false));
+            OFB_TRY(run_pairs_chunk(c, cfg, c->pair_pyr[slot][0], seq ? c->pair_pyr[slot][0] : c->pair_pyr[slot][1], n, c0,
+                                    (const ofb_imu_sample*)dimu, counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
         }
         ctx->launches += tw->launches - tw0;
         OFB_CUDA(cudaEventRecord(ctx->ev_twin_join, tw->stream));
@@ -224,10 +230,12 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
         return ofb_finish_out(ctx, o, 4);
     }
     // resident frames (or a small batch): one pass over the whole batch
-    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][0], prev, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
-    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][1], next, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
-    OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[0][0], ctx->pair_pyr[0][1], n_pairs, 0, (const ofb_imu_sample*)dimu, counts_in,
-                            d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, ctx->profile));
+    OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][0], prev, w, h, pitch, image_stride, seq ? n_pairs + 1 : n_pairs,
+                            seq ? n_pairs + 1 : n_pairs, cfg->max_level, false));
+    if (!seq)
+        OFB_TRY(ofb_pyr_prepare(ctx, &ctx->pair_pyr[0][1], next, w, h, pitch, image_stride, n_pairs, n_pairs, cfg->max_level, false));
+    OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[0][0], seq ? ctx->pair_pyr[0][0] : ctx->pair_pyr[0][1], n_pairs, 0,
+                            (const ofb_imu_sample*)dimu, counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, ctx->profile));
     int rc = ofb_finish_out(ctx, o, 4);
     if (rc == OFB_OK && ctx->profile) {
         // stage order: 0 pyramids, 1 lambda_min+NMS, 2 ordered selection, 3 LK, 4 solve

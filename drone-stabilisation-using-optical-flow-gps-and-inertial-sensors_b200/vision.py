@@ -222,3 +222,14 @@ def frame_pairs(prev, nxt, imu, cfg, pts_in=None, n_in=None, want_tracks=False, 
     if want_tracks:
         return res, pp, pn, st
     return res
+
+
+def frame_sequence(frames, imu, cfg, want_tracks=False, ctx=None):
+    """One camera stream: frames (N+1,H,W) uint8 -> N consecutive pairs (frame i, frame i+1), as
+    velocity_measurment_node:224-267 sees them (it keeps the previous callback's image). Passing the two views
+    of ONE buffer lets the library upload every frame and build its pyramid once (`next == prev + image_stride`
+    is the C ABI's sequence layout, include/ofb200.h)."""
+    if isinstance(frames, np.ndarray):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    return frame_pairs(frames[:-1], frames[1:], imu, cfg, want_tracks=want_tracks, ctx=ctx)
+

@@ -176,7 +176,11 @@ typedef struct {
 /* prev/next: n_pairs images each, image i at base + i*image_stride (host or device).
  * pts_in (detect==0): n_pairs x max_corners x 2 float32 with counts n_in[n_pairs].
  * Optional outputs (may be NULL): prev_pts/next_pts (n_pairs x max_corners x 2 f32),
- * status (n_pairs x max_corners u8). */
+ * status (n_pairs x max_corners u8).
+ * Sequence layout: when next == prev + image_stride the n_pairs+1 images are consecutive frames of one
+ * camera stream (pair i = frames i, i+1 -- what the node sees, it keeps the previous callback's image,
+ * velocity_measurment_node:224-267 `old_gray`); every frame is then uploaded and its pyramid built once.
+ * Results are identical to passing the same pairs in two separate buffers. */
 int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pairs,
                     const uint8_t* prev, const uint8_t* next, int pitch, size_t image_stride,
                     const ofb_imu_sample* imu, const float* pts_in, const int* n_in,

@@ -312,3 +312,35 @@ def test_mc_without_error_bound_gives_identical_velocities(ctx, pos50):
         assert np.all(R2 == 0) and np.all(R1 > 0)
         np.testing.assert_allclose(s1["sum_dv"], s2["sum_dv"], rtol=1e-3, atol=300 * tol)
         assert s2["sum_R"][0] == 0
+
+
+def test_frame_sequence_equals_independent_pairs(ctx):
+    """Sequence layout (next == prev + image_stride: consecutive frames of one stream in one buffer) uploads every
+    frame and builds its pyramid once; the results must be bit-identical to the same pairs passed as two buffers,
+    for host frames (pipelined sub-batches of 16 pairs + 1 frame) and for device-resident frames (twin chunks)."""
+    import ofb200
+    import torch
+    a0, b0, mo = synth.make_pair(120, 160, 3, 7, max_disp=4.0)
+    a1, b1, _ = synth.make_pair(120, 160, 3, 9, max_disp=3.0)
+    # ping-pong chains: every consecutive pair is a small known motion
+    frames = np.stack(([a0, b0] * 6 + [a1, b1] * 6)[:22] + [a1])       # 23 frames -> 22 pairs (12th pair jumps)
+    n = len(frames) - 1
+    K = 48
+    cfg = ofb200.make_pair_cfg(160, 120, K, 0.01, 6, 5, (15, 15), 2, (3, 20, 0.03), variant="node",
+                               principal=(mo["cx"], mo["cy"]), pos_scale=1.0 / mo["f"], flow_scale=1.0 / (mo["f"] * mo["dt"]))
+    imu = np.zeros(n, ofb200._lib.IMU_DTYPE)
+    imu["d"][:], imu["n"][:], imu["w"][:] = mo["d"], mo["n"], mo["w"]
+    prev_c, next_c = frames[:-1].copy(), frames[1:].copy()           # separate buffers: independent-pair path
+    ref = ofb200.frame_pairs(prev_c, next_c, imu, cfg, want_tracks=True, ctx=ctx)
+    for rep in range(2):
+        seq = ofb200.frame_sequence(frames, imu, cfg, want_tracks=True, ctx=ctx)
+    tf = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
+    seq_d = ofb200.frame_sequence(tf, imu, cfg, want_tracks=True, ctx=ctx)
+    short = ofb200.frame_sequence(frames[:4], imu[:3], cfg, want_tracks=True, ctx=ctx)     # single-pass path
+    for got, sl in ((seq, slice(None)), (seq_d, slice(None)), (short, slice(0, 3))):
+        for name in ("v", "s", "res", "rank", "n_features", "n_tracked"):
+            assert np.array_equal(got[0][name], ref[0][name][sl]), name
+        for k in (1, 2, 3):
+            assert np.array_equal(got[k], ref[k][sl])
+    assert (ref[0]["n_tracked"][:10] > 10).all()
