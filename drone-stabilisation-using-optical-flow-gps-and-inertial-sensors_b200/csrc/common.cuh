@@ -86,6 +86,7 @@ struct ofb_ctx {
     // host-input pipelining of ofb_frame_pairs: H2D of sub-batch i+1 on copy_stream overlaps compute of sub-batch i
     cudaStream_t copy_stream = nullptr;
     cudaStream_t upload_stream = nullptr;        // stream level-0 uploads go to (nullptr = stream)
+    const uint8_t* upload_first_dev = nullptr;   // when set, image 0 of the next level-0 upload is copied from this device frame
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // the ordered-selection kernel occupies one CTA per image; the pyramid kernels of the same batch run beside
     // it on aux_stream (fork after the lambda_min kernel, join before LK)

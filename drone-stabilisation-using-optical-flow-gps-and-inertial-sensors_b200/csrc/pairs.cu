@@ -159,7 +159,7 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     const bool host_frames = !ofb_is_device_ptr(prev) && !ofb_is_device_ptr(next);
     // consecutive frames of one stream in one buffer: each frame is uploaded and its pyramid built once per sub-batch
     const bool seq = next == prev + image_stride && n_pairs > 1;
-    const int chunk = seq ? 16 : 8;
+    const int chunk = 8;
     if (host_frames && n_pairs > chunk && !ctx->profile) {
         // Host frames: pipeline sub-batches. The H2D copy of sub-batch i+1 runs on copy_stream into the other
         // workspace slot while sub-batch i computes on the context stream.
@@ -179,8 +179,14 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
             const int slot = ci & 1;
             OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));
             ctx->upload_stream = ctx->copy_stream;
+            // sequence layout: the first frame of this sub-batch is the last frame of the previous one, which sits in the
+            // other slot (same geometry, owned level 0) -- a device copy instead of a second trip over PCIe
+            const ofb_pyr* other = ctx->pair_pyr[slot ^ 1][0];
+            if (seq && ci > 0 && other && other->level0_owned && other->w[0] == w && other->h[0] == h)
+                ctx->upload_first_dev = other->base + other->level_off[0] + (size_t)chunk * other->image_stride[0];
             int r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
                                     seq ? n + 1 : n, seq ? chunk + 1 : chunk, cfg->max_level, false);
+            ctx->upload_first_dev = nullptr;
             if (r == OFB_OK && !seq)
                 r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
                                     chunk, cfg->max_level, false);
