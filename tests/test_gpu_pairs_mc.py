@@ -97,6 +97,20 @@ def test_frame_pairs_track_only_and_variants(ctx):
     u = (pn[0, :n][ok] - pp[0, :n][ok]).astype(np.float64) / (mo["f"] * mo["dt"])
     vref = vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], t, variant="exp")[0]
     assert np.abs(res["v"][0] - vref).max() <= 1e-4 * np.abs(vref).max()
+    # the same pair five times as one batch: host frames, device-resident frames (twin-context chunks) and the
+    # sequence layout (a, b, a, b, ...: even pairs are this pair) must all reproduce the single-pair result
+    import torch
+    B = 5
+    imu5 = np.repeat(imu, B); pin5 = np.repeat(pin, B, axis=0); nin5 = [len(pts)] * B
+    a5, b5 = np.stack([a] * B), np.stack([b] * B)
+    r_h = ofb200.frame_pairs(a5, b5, imu5, cfg, pts_in=pin5, n_in=nin5, want_tracks=True, ctx=ctx)
+    r_d = ofb200.frame_pairs(torch.from_numpy(a5).cuda(), torch.from_numpy(b5).cuda(), imu5, cfg, pts_in=pin5, n_in=nin5,
+                             want_tracks=True, ctx=ctx)
+    seq = torch.from_numpy(np.stack([a, b] * 3)).cuda()                  # 6 frames -> 5 pairs
+    r_s = ofb200.frame_pairs(seq[:-1], seq[1:], imu5, cfg, pts_in=pin5, n_in=nin5, want_tracks=True, ctx=ctx)
+    for r, idx in ((r_h, range(B)), (r_d, range(B)), (r_s, (0, 2, 4))):
+        for i in idx:
+            assert np.array_equal(r[0]["v"][i], res["v"][0]) and np.array_equal(r[2][i], pn[0]) and np.array_equal(r[3][i], st[0])
 
 
 # ---- Monte-Carlo -----------------------------------------------------------------------------------

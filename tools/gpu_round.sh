@@ -11,13 +11,15 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpur
 echo "bench exit $?" >> gpurun_out/bench.err
 tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; tail -c 2500 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
-  PROF="python tools/profile_pairs.py --batch 8 --steps 2 --mc-trials 2000000"
+  # whole-batch launches (no twin-context chunking), 32 pairs per launch as in the bench
+  export OFB_TWIN_CHUNKS=0
+  PROF="python tools/profile_pairs.py --batch 32 --steps 2 --mc-trials 2000000"
   timeout 300 $PROF > gpurun_out/prof_plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
   # launch list of the bench command itself (the same command line as the bench.log above, plus --no-cpu to keep
   # the host-only CPU baseline out of the profiled run)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/ncu_bench_list.log 2>&1
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'eig_|lk_track|pyr_down|select_kernel|mc_sweep|pair_solve' -c 15 -f -o gpurun_out/prof $PROF > gpurun_out/ncu_full.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/bench_launches.csv env -u OFB_TWIN_CHUNKS python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/ncu_bench_list.log 2>&1
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'eig_|lk_track|pyr_down|select_kernel|mc_sweep|pair_solve' -c 14 -f -o gpurun_out/prof $PROF > gpurun_out/ncu_full.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'mc_sweep' -c 2 -f -o gpurun_out/prof_mc $PROF > gpurun_out/ncu_mc.log 2>&1
   tail -3 gpurun_out/prof_plain.log; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/
 fi
