@@ -467,10 +467,11 @@ def main():
     e2e_s, r = e2e_run(lambda: ofb200.frame_sequence(h_seq, imu_seq, cfg, ctx=ctx))
     e2e_i, _ = e2e_run(lambda: ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx))
     clk.__exit__()
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int((B + 1) * P + imu_seq.nbytes),
-           "d2h_bytes_per_step": int(r.nbytes), "h2d_gbs": round((B + 1) * P * args.steps / e2e_s / 1e9, 1)}
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s",
+           "h2d_bytes_per_step": int(world * ((B + 1) * P + imu_seq.nbytes)), "d2h_bytes_per_step": int(world * r.nbytes),
+           "h2d_gbs_per_gpu": round((B + 1) * P * args.steps / e2e_s / 1e9, 1)}
     independent = {"value": world * B * args.steps / (ms_ind * 1e-3), "ms_per_step": ms_ind / args.steps,
-                   "e2e": world * B * args.steps / e2e_i, "h2d_bytes_per_step": int(2 * B * P + imu.nbytes),
+                   "e2e": world * B * args.steps / e2e_i, "h2d_bytes_per_step": int(world * (2 * B * P + imu.nbytes)),
                    "max_abs_v_error_vs_truth": float(verr_i),
                    "note": "same pairs as separate prev/next buffers (no frame shared between pairs)"}
 
