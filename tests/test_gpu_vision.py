@@ -281,3 +281,33 @@ def test_two_kernel_variants_agree(ctx):
             on, os_, oe = io.pyrlk(a, b, pts, win, 3, (3, 20, 0.03))
             assert np.array_equal(s1, os_)
             assert np.abs(n1 - on)[ok].max() <= 5e-3
+
+
+def test_marching_kernel_shapes_vs_generic(ctx):
+    """Strip/band decomposition of the marching lambda_min kernel: widths around the strip pitch (128-bs-1 columns),
+    heights around the band height, aligned and unaligned pitches, multi-image batches -- maps and candidate-derived
+    feature lists must be bit-identical to the generic kernel's (same exact integer sums, same fp32 expression)."""
+    import ofb200
+    rng = np.random.default_rng(11)
+    shapes = [(48, 96), (49, 97), (64, 120), (65, 121), (100, 239), (100, 240), (100, 241), (77, 360), (203, 476),
+              (301, 488), (150, 1000), (111, 1284)]
+    for k, (h, w) in enumerate(shapes):
+        img = synth.texture(h, w, 40 + k)
+        if k % 3 == 0:                                   # flat borders and a saturated block: plateaus, zero gradients
+            img[:, :5] = 17; img[-4:, :] = 200; img[h // 3:h // 3 + 9, w // 4:w // 4 + 30] = 255
+        bs = (3, 7, 12)[k % 3]
+        q = float(rng.choice([0.01, 0.05, 0.2]))
+        fast = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
+        pts_fast = ofb200.goodFeaturesToTrack(img, 500, q, 5, blockSize=bs, ctx=ctx)
+        os.environ["OFB_EIG_GENERIC"] = "1"
+        try:
+            gen = ofb200.cornerMinEigenVal(img, bs, ctx=ctx)
+            pts_gen = ofb200.goodFeaturesToTrack(img, 500, q, 5, blockSize=bs, ctx=ctx)
+        finally:
+            os.environ["OFB_EIG_GENERIC"] = "0"
+        assert np.array_equal(fast, gen), (h, w, bs, np.argwhere(fast != gen)[:4])
+        assert np.array_equal(as_list(pts_fast), as_list(pts_gen)), (h, w, bs)
+        # and against the CPU oracle's map within the documented tie tolerance
+        ref = io.min_eig_map(img, bs)
+        tol = 2.0 * bs * 2.0 ** -23 * half_trace_max(img, bs)
+        assert np.abs(fast - ref).max() <= tol, (h, w, bs, np.abs(fast - ref).max(), tol)
