@@ -161,43 +161,62 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     const bool seq = next == prev + image_stride && n_pairs > 1;
     const int chunk = 8;
     if (host_frames && n_pairs > chunk && !ctx->profile) {
-        // Host frames: pipeline sub-batches. The H2D copy of sub-batch i+1 runs on copy_stream into the other
-        // workspace slot while sub-batch i computes on the context stream.
-        if (!ctx->copy_stream) {
-            OFB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (int s = 0; s < 2; ++s) {
-                OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[s], cudaEventDisableTiming));
-                OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[s], cudaEventDisableTiming));
-            }
+        // Host frames: pipeline sub-batches. All uploads go to one copy stream (the PCIe copy is the bound); the
+        // sub-batches compute alternately on this context and on its twin (own stream, scratch and two workspace
+        // slots each), so the one-CTA-per-image selection of sub-batch i runs beside the lambda_min kernel of
+        // sub-batch i+1. The last sub-batches are smaller: what remains after the last copy is one short chain.
+        if (!ctx->twin) {
+            OFB_TRY(ofb_ctx_create(ctx->device, &ctx->twin));
+            OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_twin_fork, cudaEventDisableTiming));
+            OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_twin_join, cudaEventDisableTiming));
         }
-        // copies must not start before earlier work on the context stream that may still read the slots
-        OFB_CUDA(cudaEventRecord(ctx->ev_free[0], ctx->stream));
-        OFB_CUDA(cudaEventRecord(ctx->ev_free[1], ctx->stream));
-        int ci = 0;
-        for (int c0 = 0; c0 < n_pairs; c0 += chunk, ++ci) {
-            const int n = n_pairs - c0 < chunk ? n_pairs - c0 : chunk;
-            const int slot = ci & 1;
-            OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[slot], 0));
-            ctx->upload_stream = ctx->copy_stream;
-            // sequence layout: the first frame of this sub-batch is the last frame of the previous one, which sits in the
-            // other slot (same geometry, owned level 0) -- a device copy instead of a second trip over PCIe
-            const ofb_pyr* other = ctx->pair_pyr[slot ^ 1][0];
-            if (seq && ci > 0 && other && other->level0_owned && other->w[0] == w && other->h[0] == h)
-                ctx->upload_first_dev = other->base + other->level_off[0] + (size_t)chunk * other->image_stride[0];
-            int r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
+        ofb_ctx* tw = ctx->twin;
+        if (!ctx->copy_stream) OFB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (ofb_ctx* c : {ctx, tw})
+            for (int s = 0; s < 2; ++s)
+                if (!c->ev_ready[s]) {
+                    OFB_CUDA(cudaEventCreateWithFlags(&c->ev_ready[s], cudaEventDisableTiming));
+                    OFB_CUDA(cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming));
+                }
+        // staged inputs (IMU samples, seed points) were enqueued on this context's stream
+        OFB_CUDA(cudaEventRecord(ctx->ev_twin_fork, ctx->stream));
+        OFB_CUDA(cudaStreamWaitEvent(tw->stream, ctx->ev_twin_fork, 0));
+        // copies must not start before earlier work that may still read the slots
+        for (ofb_ctx* c : {ctx, tw})
+            for (int s = 0; s < 2; ++s) OFB_CUDA(cudaEventRecord(c->ev_free[s], c->stream));
+        const uint64_t tw0 = tw->launches;
+        const ofb_pyr* last = nullptr;    // previous sub-batch's pyramid (sequence layout: holds this one's first frame)
+        int last_n = 0, ci = 0;
+        for (int c0 = 0; c0 < n_pairs; ++ci) {
+            const int left = n_pairs - c0;
+            const int n = left > 12 ? chunk : left > 4 ? 4 : left > 2 ? 2 : left;
+            ofb_ctx* c = (ci & 1) ? tw : ctx;
+            const int slot = (ci >> 1) & 1;
+            OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, c->ev_free[slot], 0));
+            c->upload_stream = ctx->copy_stream;
+            // sequence layout: the first frame of this sub-batch is the last frame of the previous one, already in HBM
+            // (same geometry, owned level 0) -- a device copy instead of a second trip over PCIe
+            if (seq && last && last->level0_owned && last->w[0] == w && last->h[0] == h)
+                c->upload_first_dev = last->base + last->level_off[0] + (size_t)last_n * last->image_stride[0];
+            int r = ofb_pyr_prepare(c, &c->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
                                     seq ? n + 1 : n, seq ? chunk + 1 : chunk, cfg->max_level, false);
-            ctx->upload_first_dev = nullptr;
+            c->upload_first_dev = nullptr;
             if (r == OFB_OK && !seq)
-                r = ofb_pyr_prepare(ctx, &ctx->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
+                r = ofb_pyr_prepare(c, &c->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
                                     chunk, cfg->max_level, false);
-            ctx->upload_stream = nullptr;
+            c->upload_stream = nullptr;
             OFB_TRY(r);
-            OFB_CUDA(cudaEventRecord(ctx->ev_ready[slot], ctx->copy_stream));
-            OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[slot], 0));
-            OFB_TRY(run_pairs_chunk(ctx, cfg, ctx->pair_pyr[slot][0], seq ? ctx->pair_pyr[slot][0] : ctx->pair_pyr[slot][1], n, c0,
+            OFB_CUDA(cudaEventRecord(c->ev_ready[slot], ctx->copy_stream));
+            OFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+            OFB_TRY(run_pairs_chunk(c, cfg, c->pair_pyr[slot][0], seq ? c->pair_pyr[slot][0] : c->pair_pyr[slot][1], n, c0,
                                     (const ofb_imu_sample*)dimu, counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
-            OFB_CUDA(cudaEventRecord(ctx->ev_free[slot], ctx->stream));
+            OFB_CUDA(cudaEventRecord(c->ev_free[slot], c->stream));
+            last = c->pair_pyr[slot][0]; last_n = n;
+            c0 += n;
         }
+        ctx->launches += tw->launches - tw0;
+        OFB_CUDA(cudaEventRecord(ctx->ev_twin_join, tw->stream));
+        OFB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_twin_join, 0));
         return ofb_finish_out(ctx, o, 4);
     }
     // Resident frames: the batch is cut into chunks that alternate between this context and a twin context with its own
