@@ -135,6 +135,20 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+WORKLOAD = ("C2: single 1920x1080 stream, consecutive frame pairs, 1000 features, maxLevel 4, "
+            "detect+track+solve")
+
+
+def stream_pair(pairs, k):
+    """Pair k of the synthetic single stream (frame k, frame k+1): the stream alternates the base view with moved
+    views, so even pairs are motion k/2 forward and odd pairs the way back (gyro rate negated)."""
+    a, b, mo = pairs[(k // 2) % len(pairs)]
+    if k % 2 == 0:
+        return a, b, mo
+    back = dict(mo); back["w"] = -np.asarray(mo["w"])
+    return b, a, back
+
+
 def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
     """The reference's CPU path on identical frames: cv2 gftt + LK + Python solve_lgs (oracle port)."""
     import cv2
@@ -143,7 +157,7 @@ def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
     done, t0 = 0, time.perf_counter()
     split = np.zeros(3)
     while True:
-        a, b, mo = pairs[done % len(pairs)]
+        a, b, mo = stream_pair(pairs, done)
         t1 = time.perf_counter()
         p = cv2.goodFeaturesToTrack(a, K_FEAT, QUALITY, MIN_DIST, blockSize=BLOCK)
         t2 = time.perf_counter()
@@ -182,8 +196,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": "C2: 1920x1080 frame pairs, 1000 features, maxLevel 4, detect+track+solve",
-                       "pairs_per_step": args.ref_pairs},
+            "config": {"workload": WORKLOAD, "pairs_per_step": args.ref_pairs},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": ncores, "kind": "port",
                              "sample": "%d pairs: cv2 4.13 goodFeaturesToTrack+calcOpticalFlowPyrLK + oracle port of the "
                                        "reference's Python solve_lgs, all host threads; ms gftt/LK/solve = %s" %
@@ -328,13 +341,12 @@ def main():
     # consecutive pair is a small, known camera motion.
     h_seq = ctx.pinned_array((B + 1, H, W), np.uint8)
     imu_seq = np.zeros(B, ofb200._lib.IMU_DTYPE)
-    for k in range(B + 1):
-        j = (k // 2) % len(pairs)
-        h_seq[k] = pairs[j][0] if k % 2 == 0 else pairs[j][1]
     for k in range(B):
-        mo = pairs[(k // 2) % len(pairs)][2]
-        imu_seq["d"][k], imu_seq["n"][k] = mo["d"], mo["n"]
-        imu_seq["w"][k] = mo["w"] if k % 2 == 0 else -np.asarray(mo["w"])
+        fa, fb, mo = stream_pair(pairs, k)
+        h_seq[k] = fa
+        if k == B - 1:
+            h_seq[B] = fb
+        imu_seq["d"][k], imu_seq["n"][k], imu_seq["w"][k] = mo["d"], mo["n"], mo["w"]
     d_seq = torch.empty((B + 1, H, W), dtype=torch.uint8, device="cuda")
     ctx.memcpy(d_seq, h_seq, h_seq.nbytes)
     d_imu_seq = torch.from_numpy(imu_seq.view(np.uint8).reshape(-1).copy()).cuda()
@@ -535,8 +547,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-                "config": {"workload": "C2: single 1920x1080 stream, consecutive frame pairs, 1000 features, maxLevel 4, "
-                                       "detect+track+solve",
+                "config": {"workload": WORKLOAD,
                            "pairs_per_step_per_gpu": B, "frames_per_step_per_gpu": B + 1, "distinct_motions": len(pairs),
                            "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
                            "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
