@@ -414,6 +414,44 @@ def main():
     ctx.memcpy(res_i, d_res, res_i.nbytes)
     verr_i = max(np.abs(res_i["v"][i] - pairs[i % len(pairs)][2]["v"]).max() for i in range(B))
 
+    # steady state of the callers (they re-detect only when features run low: evaluate_exp.py:105-107, node:157-163):
+    # track+solve of given points -- pyramid, LK and solve, no detection. The points are the detector's output for
+    # the same stream, left on the device by one detect pass.
+    d_pts = torch.zeros((B, K_FEAT, 2), dtype=torch.float32, device="cuda")
+    ofb200._lib.check(lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, d_seq.data_ptr(), d_seq.data_ptr() + P, W, W * H,
+                                          ofb200._lib.ptr(d_imu_seq), None, None, ofb200._lib.ptr(d_res), d_pts.data_ptr(), None, None))
+    ctx.sync()
+    res_t = np.zeros(B, ofb200._lib.RESULT_DTYPE)
+    ctx.memcpy(res_t, d_res, res_t.nbytes)
+    d_nin = torch.from_numpy(res_t["n_features"].astype(np.int32)).cuda()
+    cfg_t = ofb200.make_pair_cfg(W, H, K_FEAT, QUALITY, MIN_DIST, BLOCK, WIN, MAX_LEVEL, CRIT, variant="node",
+                                 principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"],
+                                 flow_scale=1.0 / (mo0["f"] * mo0["dt"]), detect=False)
+    torch.cuda.synchronize()
+
+    def step_track():
+        ofb200._lib.check(lib.ofb_frame_pairs(ctx.h, C.byref(cfg_t), B, d_seq.data_ptr(), d_seq.data_ptr() + P, W, W * H,
+                                              ofb200._lib.ptr(d_imu_seq), d_pts.data_ptr(), d_nin.data_ptr(),
+                                              ofb200._lib.ptr(d_res), None, None, None))
+
+    for _ in range(args.warmup):
+        step_track()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_track()
+    ms_trk = ctx.timer_stop()
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms_trk], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_trk = float(t.item())
+    res_k = np.zeros(B, ofb200._lib.RESULT_DTYPE)
+    ctx.memcpy(res_k, d_res, res_k.nbytes)
+    track_solve = {"value": world * B * args.steps / (ms_trk * 1e-3), "unit": "pairs/s", "ms_per_step": ms_trk / args.steps,
+                   "max_abs_v_diff_vs_detect_mode": float(np.abs(res_k["v"] - res_t["v"]).max()),
+                   "note": "track+solve of given points (pyramid, LK, solve; no detection), resident frames"}
+
     # per-stage durations (CUDA events between the kernels of the same call path)
     ctx.set_profile(True)
     for _ in range(3):                     # the profiled call path sizes its own scratch on first use
@@ -552,7 +590,7 @@ def main():
                            "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
                            "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk.summary(), "independent_pairs": independent, "mc": mc,
+                "clocks": clk.summary(), "independent_pairs": independent, "track_solve": track_solve, "mc": mc,
                 "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
         print(json.dumps(line))
     if dist is not None:
