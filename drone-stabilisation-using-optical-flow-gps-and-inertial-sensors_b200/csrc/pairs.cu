@@ -1,6 +1,11 @@
 // pairs.cu -- fused frame-pair path: pyramid -> Shi-Tomasi -> pyramidal LK -> velocity solve for a
-// batch of independent frame pairs, everything enqueued on the context's stream with no host
-// round-trip between stages (feature counts stay on the device).
+// batch of independent frame pairs (or of consecutive frames of one stream), with no host round-trip
+// between stages (feature counts stay on the device). Work is ordered on the context's stream; inside a
+// call it fans out to helper streams and joins back before the call's results are read:
+//   * aux streams: the pyramid kernels run beside the one-CTA-per-image selection kernel;
+//   * twin context (own stream + scratch): every other chunk of a batch, so the selection/pyramid phase of
+//     one chunk hides behind the lambda_min kernel of the next;
+//   * copy stream: host frames are uploaded in sub-batches while the previous sub-batch computes.
 //
 // Replaces the per-frame dataflow of velocity_measurment_node:224-267 (centre with of.pix_trans,
 // scale by `scaling`, solve_lgs) and flight_experiments/evaluate_exp.py:77-120
