@@ -52,8 +52,8 @@ def parse():
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-pairs", type=int, default=4, help="pairs per step of the reference arm")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
-                    help="c2 (default, the headline line); c4 = 3840x2160 single-pair latency; c5 = 256-stream 720p fleet")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"],
+                    help="c2 (default, the headline line); c1 = 640x480 and c4 = 3840x2160 single-pair latency; c5 = 256-stream 720p fleet")
     return ap.parse_args()
 
 
@@ -177,6 +177,33 @@ def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
     return done / el, done, (split / done * 1e3).tolist()
 
 
+def cpu_pair_path_generic(pairs, w, h, feat, ml, seconds):
+    """cv2 + oracle solve on pairs of another geometry (C1 / C4 latency lines)."""
+    import cv2
+    from oracle import velocity_oracle as vo
+    cv2.setNumThreads(len(os.sched_getaffinity(0)))
+    done, t0, split = 0, time.perf_counter(), np.zeros(3)
+    while True:
+        a, b, mo = pairs[done % len(pairs)]
+        t1 = time.perf_counter()
+        p = cv2.goodFeaturesToTrack(a, feat, QUALITY, MIN_DIST, blockSize=BLOCK)
+        t2 = time.perf_counter()
+        nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=WIN, maxLevel=ml, criteria=CRIT)
+        t3 = time.perf_counter()
+        ok = st.ravel() == 1
+        newp = nxt.reshape(-1, 2)[ok]
+        x = (newp.astype(np.float64) - np.array([mo["cx"], mo["cy"]])) / mo["f"]
+        u = (newp - p.reshape(-1, 2)[ok]).astype(np.float64) / (mo["f"] * mo["dt"])
+        vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], variant="node")
+        t4 = time.perf_counter()
+        split += [t2 - t1, t3 - t2, t4 - t3]
+        done += 1
+        el = time.perf_counter() - t0
+        if el >= seconds and done >= 3:
+            break
+    return done / el, done, (split / done * 1e3).tolist()
+
+
 def reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -238,6 +265,8 @@ def extra_workload(args):
     ctx = ofb200.Context(local)
     if args.workload == "c4":
         w, h, feat, ml, B, distinct = 3840, 2160, 5000, 5, 1, 2
+    elif args.workload == "c1":
+        w, h, feat, ml, B, distinct = 640, 480, 200, 3, 1, 2
     else:
         w, h, feat, ml, distinct = 1280, 720, 500, 3, 8
         B = 256 // world + (1 if rank < 256 % world else 0)
@@ -261,7 +290,7 @@ def extra_workload(args):
     ctx.sync()
     if dist is not None:
         dist.barrier()
-    if args.workload == "c4":
+    if args.workload in ("c4", "c1"):
         lat = []
         for _ in range(max(args.steps, 50)):
             ctx.timer_start(); step(); lat.append(ctx.timer_stop())
@@ -275,10 +304,27 @@ def extra_workload(args):
             step()
         sms, calls = ctx.stage_times()
         ctx.set_profile(False)
-        line = {"metric": "3840x2160 frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
+        # the same pair from (pageable) host arrays through the public call, result read back: what a ROS callback sees
+        ha, hb = pairs[0][0], pairs[0][1]
+        for _ in range(5):
+            ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx)
+        e2e_lat = []
+        for _ in range(max(args.steps, 50)):
+            t0 = time.perf_counter(); ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx); e2e_lat.append((time.perf_counter() - t0) * 1e3)
+        cpu_ms = None
+        if not args.no_cpu:
+            try:
+                v, n_, split = cpu_pair_path_generic(pairs, w, h, feat, ml, 3.0)
+                cpu_ms = {"ms_per_pair": 1e3 / v, "ms_gftt_lk_solve": [round(x, 2) for x in split], "cores": len(os.sched_getaffinity(0))}
+            except Exception as e:
+                cpu_ms = {"unavailable": repr(e)}
+        name = "3840x2160" if args.workload == "c4" else "640x480"
+        line = {"metric": name + " frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
+                "e2e_host_call_ms_p50": float(np.percentile(e2e_lat, 50)), "cpu_reference": cpu_ms,
                 "stage_ms_serial": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s / max(calls, 1), 4) for s in sms])),
                 "unit": "ms", "p95": float(np.percentile(lat, 95)), "n_gpus": 1, "steps": len(lat), "higher_is_better": False,
-                "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call"},
+                "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call" if args.workload == "c4"
+                           else "C1: 640x480, 200 features, maxLevel 3, one resident pair per call"},
                 "check": {"n_tracked": int(res["n_tracked"][0]), "v": res["v"][0].tolist(), "truth": pairs[0][2]["v"].tolist()}}
     else:
         ctx.timer_start()
