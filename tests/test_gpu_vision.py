@@ -311,3 +311,41 @@ def test_marching_kernel_shapes_vs_generic(ctx):
         ref = io.min_eig_map(img, bs)
         tol = 2.0 * bs * 2.0 ** -23 * half_trace_max(img, bs)
         assert np.abs(fast - ref).max() <= tol, (h, w, bs, np.abs(fast - ref).max(), tol)
+
+
+def test_selection_cluster_mode_equals_single_cta(ctx):
+    """Cluster mode of the selection kernel (2/4/8 CTAs per image share the key scans through DSMEM) must return
+    exactly the single-CTA list: one chunk, many chunks (maxCorners=0 with a small minDistance), masks, no
+    min-distance, and a batch of images."""
+    import ofb200
+    cases = [(synth.texture(240, 320, 61), dict(maxCorners=200, qualityLevel=0.01, minDistance=10, blockSize=7)),
+             (synth.texture(480, 640, 62), dict(maxCorners=0, qualityLevel=0.001, minDistance=2, blockSize=3)),
+             (synth.texture(300, 500, 63), dict(maxCorners=5000, qualityLevel=0.01, minDistance=0, blockSize=7)),
+             (synth.texture(131, 517, 64), dict(maxCorners=60, qualityLevel=0.3, minDistance=20, blockSize=12))]
+    for img, kw in cases:
+        os.environ["OFB_SELECT_CLUSTER"] = "1"
+        try:
+            ref = as_list(ofb200.goodFeaturesToTrack(img, ctx=ctx, **kw))
+            for cs in ("2", "4", "8"):
+                os.environ["OFB_SELECT_CLUSTER"] = cs
+                got = as_list(ofb200.goodFeaturesToTrack(img, ctx=ctx, **kw))
+                assert np.array_equal(got, ref), (img.shape, kw, cs, len(got), len(ref))
+        finally:
+            del os.environ["OFB_SELECT_CLUSTER"]
+    assert len(ref) > 0
+    # a batch through the fused path
+    a, b, mo = synth.make_pair(240, 320, 5, 5, max_disp=4.0)
+    cfg = ofb200.make_pair_cfg(320, 240, 100, 0.01, 8, 7, (15, 15), 3, (3, 20, 0.03), variant="node",
+                               principal=(mo["cx"], mo["cy"]), pos_scale=1.0 / mo["f"], flow_scale=1.0 / (mo["f"] * mo["dt"]))
+    imu = np.zeros(3, ofb200._lib.IMU_DTYPE); imu["d"][:], imu["n"][:], imu["w"][:] = mo["d"], mo["n"], mo["w"]
+    A, B = np.stack([a, b, a]), np.stack([b, a, b])
+    out = {}
+    for cs in ("1", "8"):
+        os.environ["OFB_SELECT_CLUSTER"] = cs
+        try:
+            out[cs] = ofb200.frame_pairs(A, B, imu, cfg, want_tracks=True, ctx=ctx)
+        finally:
+            del os.environ["OFB_SELECT_CLUSTER"]
+    for k in range(1, 4):
+        assert np.array_equal(out["1"][k], out["8"][k])
+    assert np.array_equal(out["1"][0]["v"], out["8"][0]["v"])
