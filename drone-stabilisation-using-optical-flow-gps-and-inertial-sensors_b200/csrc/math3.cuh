@@ -34,13 +34,20 @@ OFB_HD uint4 ofb_philox4x32_10(uint4 c, uint2 k)
 // fp32 path uses the SFU intrinsics on device; the fp64 path is used for parity runs.
 OFB_HD void ofb_box_muller(uint32_t r0, uint32_t r1, float& z0, float& z1)
 {
-    float u0 = ((float)r0 + 0.5f) * 2.3283064365386963e-10f;
-    float u1 = ((float)r1 + 0.5f) * 2.3283064365386963e-10f;
 #ifdef __CUDA_ARCH__
-    float rad = sqrtf(-2.0f * __logf(u0));
+    // (float)r * 2^-32 + 2^-33 in one FMA: bit-identical to ((float)r + 0.5f) * 2^-32 (below 2^24 both are exact,
+    // above it the half is below half an ulp either way)
+    const float u0 = fmaf((float)r0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u1 = fmaf((float)r1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    // radius: -2 ln u = (-2 ln 2) lg2 u, square root by the SFU (MUFU.LG2, FMUL, MUFU.SQRT: ~1 ulp, as accurate as
+    // the fast logarithm in front of it; the IEEE sqrtf sequence with its range-check branch cost 5x as much)
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u0)));
     float s, c;
     __sincosf(6.2831853071795865f * (u1 - 0.5f), &s, &c);
 #else
+    float u0 = ((float)r0 + 0.5f) * 2.3283064365386963e-10f;
+    float u1 = ((float)r1 + 0.5f) * 2.3283064365386963e-10f;
     float rad = sqrtf(-2.0f * logf(u0));
     float a = 6.2831853071795865f * (u1 - 0.5f);
     float s = sinf(a), c = cosf(a);
