@@ -520,13 +520,14 @@ def main():
            (17 * nfeat + 80) * B]
     dom = int(np.argmax(stage_ms))
     # DRAM bytes per image of each stage's kernel(s) from the committed ncu --set full capture (profiles/)
-    traffic, issue_pct = None, None
+    traffic, issue_pct, winst = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = ["pyramid", "eig_nms", "select", "lk", "solve"][dom]
         if tj.get(key) is not None:
             traffic = float(tj[key]["dram_bytes_per_pair"]) * B
             issue_pct = tj[key].get("issue_active_pct")
+            winst = tj[key].get("warp_inst_per_pair")
     except Exception:
         pass
     peaks = {}
@@ -541,7 +542,7 @@ def main():
                 "stage_ms": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s, 4) for s in stage_ms])),
                 "stage_gbs": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"],
                                       [round(a / (s * 1e-3) / 1e9, 2) if s > 0 else None for a, s in zip(alg, stage_ms)])),
-                "issue_active_pct_ncu": issue_pct,
+                "issue_active_pct_ncu": issue_pct, "issue": None,
                 "note": "the two dominant kernels (lambda_min+NMS, LK) are warp-issue bound (ncu issue-active 77 % / 79 %), "
                         "not HBM bound: their DRAM traffic is the image read once; see DESIGN.md section 6"}
 
@@ -627,6 +628,15 @@ def main():
         except Exception as e:   # cv2 missing on the box
             cpu = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "port", "sample": "unavailable: %r" % (e,)}
 
+    # the dominant kernel against the bound that actually limits it: warp-instruction issue (instruction count per
+    # pair from the committed ncu capture, live stage time, live SM clock, 4 schedulers per SM)
+    clocks = clk.summary()
+    if winst and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        peak_i = sms * 4 * float(clocks["sm_mhz"]) * 1e6
+        ach_i = float(winst) * B / (stage_ms[dom] * 1e-3)
+        roofline["issue"] = {"achieved": ach_i, "peak": peak_i, "unit": "warp-instructions/s", "frac": ach_i / peak_i,
+                             "warp_inst_per_pair": winst}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -636,7 +646,7 @@ def main():
                            "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
                            "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk.summary(), "independent_pairs": independent, "track_solve": track_solve, "mc": mc,
+                "clocks": clocks, "independent_pairs": independent, "track_solve": track_solve, "mc": mc,
                 "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
         print(json.dumps(line))
     if dist is not None:
