@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--mc-trials", type=int, default=MC_TOTAL)
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ref-pairs", type=int, default=4, help="pairs per step of the reference arm")
+    ap.add_argument("--ref-pairs", type=int, default=16, help="pairs per step of the reference arm")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"],
                     help="c2 (default, the headline line); c1 = 640x480 and c4 = 3840x2160 single-pair latency; c5 = 256-stream 720p fleet")
     return ap.parse_args()
