@@ -330,8 +330,14 @@ def test_selection_cluster_mode_equals_single_cta(ctx):
                 os.environ["OFB_SELECT_CLUSTER"] = cs
                 got = as_list(ofb200.goodFeaturesToTrack(img, ctx=ctx, **kw))
                 assert np.array_equal(got, ref), (img.shape, kw, cs, len(got), len(ref))
+            # the block size (chunk of 512 / 1024 / 2048 keys, normally chosen from maxCorners) must not matter either
+            for ts, cs in (("256", "1"), ("512", "1"), ("1024", "1"), ("256", "8"), ("512", "4")):
+                os.environ["OFB_SELECT_THREADS"], os.environ["OFB_SELECT_CLUSTER"] = ts, cs
+                got = as_list(ofb200.goodFeaturesToTrack(img, ctx=ctx, **kw))
+                assert np.array_equal(got, ref), (img.shape, kw, ts, cs, len(got), len(ref))
         finally:
             del os.environ["OFB_SELECT_CLUSTER"]
+            os.environ.pop("OFB_SELECT_THREADS", None)
     assert len(ref) > 0
     # a batch through the fused path
     a, b, mo = synth.make_pair(240, 320, 5, 5, max_disp=4.0)
