@@ -57,6 +57,18 @@ def parse():
     return ap.parse_args()
 
 
+def bind_near_gpu(index):
+    """Multi-GPU hosts: run this rank (and first-touch its pinned frame buffers) on the CPUs NVML reports as closest to
+    its GPU, so that the end-to-end copies do not cross the socket interconnect. Best effort: ignored where the
+    container's cpuset does not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 def make_data(distinct, rank):
     import synth
     pairs = [synth.make_pair(H, W, stream_id=rank, pair_id=100 * rank + i) for i in range(distinct)]
@@ -363,6 +375,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    bind_near_gpu(local)
     ctx = ofb200.Context(local)
     B = args.batch
     pairs = make_data(args.distinct, rank)
