@@ -66,6 +66,7 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
         if (ctx->ev_ready[s]) cudaEventDestroy(ctx->ev_ready[s]);
         if (ctx->ev_free[s]) cudaEventDestroy(ctx->ev_free[s]);
     }
+    for (cudaEvent_t e : ctx->ev_piece) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

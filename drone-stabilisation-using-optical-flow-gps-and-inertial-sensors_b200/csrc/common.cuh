@@ -70,7 +70,7 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { OFB_NSCRATCH = 24, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6 };
+enum { OFB_NSCRATCH = 25, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6 };
 
 struct ofb_ctx {
     int device = 0;
@@ -86,8 +86,8 @@ struct ofb_ctx {
     // host-input pipelining of ofb_frame_pairs: H2D of sub-batch i+1 on copy_stream overlaps compute of sub-batch i
     cudaStream_t copy_stream = nullptr;
     cudaStream_t upload_stream = nullptr;        // stream level-0 uploads go to (nullptr = stream)
-    const uint8_t* upload_first_dev = nullptr;   // when set, image 0 of the next level-0 upload is copied from this device frame
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_piece;           // one per uploaded sub-batch of a call
     // the ordered-selection kernel occupies one CTA per image; the pyramid kernels of the same batch run beside
     // it on aux_stream (fork after the lambda_min kernel, join before LK)
     cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;
@@ -108,7 +108,8 @@ enum {
     SC_IN0 = 0, SC_IN1, SC_IN2, SC_IN3, SC_IN4, SC_IN5,      // staged host inputs
     SC_OUT0, SC_OUT1, SC_OUT2, SC_OUT3,                      // staged outputs
     SC_CAND, SC_CANDCNT, SC_SEL, SC_GRID, SC_PTS0, SC_PTS1, SC_STAT, SC_ERR,
-    SC_MC0, SC_MC1, SC_MC2, SC_TMP0, SC_TMP1, SC_TMP2
+    SC_MC0, SC_MC1, SC_MC2, SC_TMP0, SC_TMP1, SC_TMP2,
+    SC_FRAMES                                                // device staging of host frames (ofb_frame_pairs)
 };
 
 struct ofb_pyr {

@@ -166,10 +166,13 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
     const bool seq = next == prev + image_stride && n_pairs > 1;
     const int chunk = 8;
     if (host_frames && n_pairs > chunk && !ctx->profile) {
-        // Host frames: pipeline sub-batches. All uploads go to one copy stream (the PCIe copy is the bound); the
-        // sub-batches compute alternately on this context and on its twin (own stream, scratch and two workspace
-        // slots each), so the one-CTA-per-image selection of sub-batch i runs beside the lambda_min kernel of
-        // sub-batch i+1. The last sub-batches are smaller: what remains after the last copy is one short chain.
+        // Host frames: pipeline sub-batches. The frames of the whole call are staged in one device buffer by
+        // back-to-back H2D copies on a copy stream (the PCIe copy is the bound: nothing else is ever queued between
+        // two copies); a sub-batch starts as soon as its frames have landed and then runs exactly the resident path
+        // (level 0 aliases the staging buffer; in the sequence layout a frame shared by two sub-batches is simply
+        // read by both). Sub-batches compute alternately on this context and on its twin (own stream and scratch),
+        // so the one-CTA-per-image selection of sub-batch i runs beside the lambda_min kernel of sub-batch i+1. The
+        // last sub-batches are smaller: what remains after the last copy is one short chain.
         if (!ctx->twin) {
             OFB_TRY(ofb_ctx_create(ctx->device, &ctx->twin));
             OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_twin_fork, cudaEventDisableTiming));
@@ -177,46 +180,62 @@ extern "C" int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pair
         }
         ofb_ctx* tw = ctx->twin;
         if (!ctx->copy_stream) OFB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (ofb_ctx* c : {ctx, tw})
-            for (int s = 0; s < 2; ++s)
-                if (!c->ev_ready[s]) {
-                    OFB_CUDA(cudaEventCreateWithFlags(&c->ev_ready[s], cudaEventDisableTiming));
-                    OFB_CUDA(cudaEventCreateWithFlags(&c->ev_free[s], cudaEventDisableTiming));
-                }
+        if (!ctx->ev_free[0]) OFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[0], cudaEventDisableTiming));
+        const int pitch_d = (w + 15) & ~15;
+        const size_t stride_d = (((size_t)pitch_d * h) + 255) & ~(size_t)255;
+        const size_t n_frames = seq ? (size_t)n_pairs + 1 : 2 * (size_t)n_pairs;
+        OFB_TRY(ctx->scratch[SC_FRAMES].reserve(stride_d * n_frames + 256));
+        uint8_t* d_frames = ctx->scratch[SC_FRAMES].as<uint8_t>();
+        uint8_t* d_prevf = d_frames;
+        uint8_t* d_nextf = seq ? d_frames + stride_d : d_frames + stride_d * (size_t)n_pairs;
+        auto upload = [&](uint8_t* dst, const uint8_t* src, int count) -> int {
+            if (count <= 0) return OFB_OK;
+            if (pitch == pitch_d && image_stride == stride_d) {            // same layout on both sides: one copy
+                OFB_CUDA(cudaMemcpyAsync(dst, src, stride_d * (size_t)(count - 1) + (size_t)pitch * (h - 1) + w,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+                return OFB_OK;
+            }
+            for (int i = 0; i < count; ++i)
+                OFB_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * stride_d, pitch_d, src + (size_t)i * image_stride, pitch, w, h,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+            return OFB_OK;
+        };
+        // the staging buffer may still be read by work enqueued earlier (a previous call with device-side outputs)
+        OFB_CUDA(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+        OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
         // staged inputs (IMU samples, seed points) were enqueued on this context's stream
         OFB_CUDA(cudaEventRecord(ctx->ev_twin_fork, ctx->stream));
         OFB_CUDA(cudaStreamWaitEvent(tw->stream, ctx->ev_twin_fork, 0));
-        // copies must not start before earlier work that may still read the slots
-        for (ofb_ctx* c : {ctx, tw})
-            for (int s = 0; s < 2; ++s) OFB_CUDA(cudaEventRecord(c->ev_free[s], c->stream));
         const uint64_t tw0 = tw->launches;
-        const ofb_pyr* last = nullptr;    // previous sub-batch's pyramid (sequence layout: holds this one's first frame)
-        int last_n = 0, ci = 0;
+        int ci = 0;
         for (int c0 = 0; c0 < n_pairs; ++ci) {
             const int left = n_pairs - c0;
             const int n = left > 12 ? chunk : left > 4 ? 4 : left > 2 ? 2 : left;
             ofb_ctx* c = (ci & 1) ? tw : ctx;
             const int slot = (ci >> 1) & 1;
-            OFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, c->ev_free[slot], 0));
-            c->upload_stream = ctx->copy_stream;
-            // sequence layout: the first frame of this sub-batch is the last frame of the previous one, already in HBM
-            // (same geometry, owned level 0) -- a device copy instead of a second trip over PCIe
-            if (seq && last && last->level0_owned && last->w[0] == w && last->h[0] == h)
-                c->upload_first_dev = last->base + last->level_off[0] + (size_t)last_n * last->image_stride[0];
-            int r = ofb_pyr_prepare(c, &c->pair_pyr[slot][0], prev + (size_t)c0 * image_stride, w, h, pitch, image_stride,
-                                    seq ? n + 1 : n, seq ? chunk + 1 : chunk, cfg->max_level, false);
-            c->upload_first_dev = nullptr;
-            if (r == OFB_OK && !seq)
-                r = ofb_pyr_prepare(c, &c->pair_pyr[slot][1], next + (size_t)c0 * image_stride, w, h, pitch, image_stride, n,
-                                    chunk, cfg->max_level, false);
-            c->upload_stream = nullptr;
-            OFB_TRY(r);
-            OFB_CUDA(cudaEventRecord(c->ev_ready[slot], ctx->copy_stream));
-            OFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ready[slot], 0));
+            if (seq) {
+                // frames c0 .. c0+n; frame c0 came with the previous sub-batch
+                const int f0 = ci == 0 ? 0 : c0 + 1;
+                OFB_TRY(upload(d_frames + (size_t)f0 * stride_d, prev + (size_t)f0 * image_stride, c0 + n + 1 - f0));
+            } else {
+                OFB_TRY(upload(d_prevf + (size_t)c0 * stride_d, prev + (size_t)c0 * image_stride, n));
+                OFB_TRY(upload(d_nextf + (size_t)c0 * stride_d, next + (size_t)c0 * image_stride, n));
+            }
+            if ((int)ctx->ev_piece.size() <= ci) {
+                cudaEvent_t e;
+                OFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->ev_piece.push_back(e);
+            }
+            OFB_CUDA(cudaEventRecord(ctx->ev_piece[ci], ctx->copy_stream));
+            OFB_CUDA(cudaStreamWaitEvent(c->stream, ctx->ev_piece[ci], 0));
+            // (c, slot) is reused every fourth sub-batch, on the same stream: stream order protects its upper levels
+            OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][0], d_prevf + (size_t)c0 * stride_d, w, h, pitch_d, stride_d,
+                                    seq ? n + 1 : n, seq ? chunk + 1 : chunk, cfg->max_level, false));
+            if (!seq)
+                OFB_TRY(ofb_pyr_prepare(c, &c->pair_pyr[slot][1], d_nextf + (size_t)c0 * stride_d, w, h, pitch_d, stride_d, n,
+                                        chunk, cfg->max_level, false));
             OFB_TRY(run_pairs_chunk(c, cfg, c->pair_pyr[slot][0], seq ? c->pair_pyr[slot][0] : c->pair_pyr[slot][1], n, c0,
                                     (const ofb_imu_sample*)dimu, counts_in, d_prev, d_next, d_stat, (ofb_pair_result*)o[3].dev, false));
-            OFB_CUDA(cudaEventRecord(c->ev_free[slot], c->stream));
-            last = c->pair_pyr[slot][0]; last_n = n;
             c0 += n;
         }
         ctx->launches += tw->launches - tw0;

@@ -312,21 +312,12 @@ int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
 static int pyr_upload_level0(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* img, int pitch, size_t image_stride)
 {
     cudaStream_t s = ctx->upload_stream ? ctx->upload_stream : ctx->stream;
-    int first = 0;
-    if (ctx->upload_first_dev) {
-        // sequence sub-batches: image 0 is the previous sub-batch's last frame, already in HBM (same layout)
-        OFB_CUDA(cudaMemcpyAsync(p->base + p->level_off[0], ctx->upload_first_dev,
-                                 (size_t)p->pitch[0] * (p->h[0] - 1) + p->w[0], cudaMemcpyDeviceToDevice, s));
-        first = 1;
-        if (p->n_active == 1) return OFB_OK;
-    }
     if (pitch == p->pitch[0] && image_stride == p->image_stride[0]) {       // same layout on both sides: one copy
-        OFB_CUDA(cudaMemcpyAsync(p->base + p->level_off[0] + (size_t)first * image_stride, img + (size_t)first * image_stride,
-                                 image_stride * (size_t)(p->n_active - 1 - first) + (size_t)pitch * (p->h[0] - 1) + p->w[0],
-                                 cudaMemcpyHostToDevice, s));
+        OFB_CUDA(cudaMemcpyAsync(p->base + p->level_off[0], img, image_stride * (size_t)(p->n_active - 1) +
+                                 (size_t)pitch * (p->h[0] - 1) + p->w[0], cudaMemcpyHostToDevice, s));
         return OFB_OK;
     }
-    for (int i = first; i < p->n_active; ++i)
+    for (int i = 0; i < p->n_active; ++i)
         OFB_CUDA(cudaMemcpy2DAsync(p->base + p->level_off[0] + (size_t)i * p->image_stride[0], p->pitch[0],
                                    img + (size_t)i * image_stride, pitch, p->w[0], p->h[0], cudaMemcpyHostToDevice, s));
     return OFB_OK;
