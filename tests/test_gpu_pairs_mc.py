@@ -283,16 +283,18 @@ def test_overlap(ctx):
     assert ofb200.overlap(a, b, ctx=ctx) == vo.overlap(a, b)
 
 
-def test_frame_pairs_pipelined_host_path_equals_resident(ctx):
-    """Host frames in batches > 8 go through the copy/compute pipeline (sub-batches, two workspace slots);
-    results must be identical to the same pairs processed one small batch at a time and to the resident path."""
+@pytest.mark.parametrize("width", [160, 161])
+def test_frame_pairs_pipelined_host_path_equals_resident(ctx, width):
+    """Host frames in batches > 8 go through the copy/compute pipeline (device staging buffer, sub-batches on the
+    context and its twin); results must be identical to the same pairs processed one small batch at a time and to
+    the resident path. Width 161: the staging pitch (176) differs from the host pitch -> per-frame 2-D copies."""
     import ofb200
     import torch
-    frames = [synth.make_pair(120, 160, s % 5, s, max_disp=4.0) for s in range(19)]
+    frames = [synth.make_pair(120, width, s % 5, s, max_disp=4.0) for s in range(19)]
     a = np.stack([f[0] for f in frames]); b = np.stack([f[1] for f in frames])
     mo0 = frames[0][2]
     K = 48
-    cfg = ofb200.make_pair_cfg(160, 120, K, 0.01, 6, 5, (15, 15), 2, (3, 20, 0.03), variant="node",
+    cfg = ofb200.make_pair_cfg(width, 120, K, 0.01, 6, 5, (15, 15), 2, (3, 20, 0.03), variant="node",
                                principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"], flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
     imu = np.zeros(len(frames), ofb200._lib.IMU_DTYPE)
     for i, f in enumerate(frames):
