@@ -346,7 +346,40 @@ def extra_workload(args):
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
-        line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",
+        # the same fleet through the device-resident feature lifecycle (ofb_tracker_step): one frame per
+        # stream and step, point sets kept on the device, masked top-up when fewer than half the features survive
+        trk = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2, n_streams=B,
+                                   feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+                                   lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
+                                   variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
+                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=ctx)
+        d_tres = torch.zeros(B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+
+        def tstep(k):
+            ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(b if k & 1 else a), w, w * h, P(d_imu), None, P(d_tres), None, None,
+                                                       None, None))
+        for k in range(2 * max(args.warmup, 1)):
+            tstep(k)
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        for k in range(2 * args.steps):
+            tstep(k)
+        tms = ctx.timer_stop()
+        tl = ctx.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([tms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tms = float(t.item())
+        tres = np.zeros(B, ofb200._lib.TRACK_RESULT_DTYPE); ctx.memcpy(tres, d_tres, tres.nbytes)
+        trk.close()
+        lifecycle = {"value": 256 * 2 * args.steps / (tms * 1e-3), "unit": "pairs/s", "ms_per_step": tms / (2 * args.steps),
+                     "gpu_launches_per_step": tl / (2 * args.steps),
+                     "what": "ofb_tracker_step: new frame -> pyramid -> LK from the kept frame -> status filter -> solve -> "
+                             "(masked top-up when <= %d points survive); resident frames" % (feat // 2),
+                     "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
+                               "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
+        line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "lifecycle": lifecycle, "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "config": {"workload": "C5: 256 streams x 1280x720, 500 features, maxLevel 3, stream-sharded", "streams_per_gpu": B},
                 "check": {"min_tracked": int(res["n_tracked"].min())}}

@@ -38,6 +38,18 @@ class PairResult(C.Structure):
                 ("n_features", C.c_int), ("n_tracked", C.c_int)]
 
 
+class TrackerCfg(C.Structure):
+    _fields_ = [("pair", PairCfg), ("n_streams", C.c_int), ("min_features", C.c_int), ("topup_mode", C.c_int),
+                ("mask_radius", C.c_int), ("bgr_input", C.c_int), ("max_speed", C.c_double),
+                ("dummy_value", C.c_double), ("gate_mode", C.c_int), ("gate_T", C.c_double), ("min_solve", C.c_int)]
+
+
+class TrackResult(C.Structure):
+    _fields_ = [("v", C.c_double * 3), ("s", C.c_double * 3), ("res", C.c_double), ("rank", C.c_int),
+                ("flags", C.c_int), ("n_prev", C.c_int), ("n_tracked", C.c_int), ("n_kept", C.c_int),
+                ("n_added", C.c_int), ("n_points", C.c_int)]
+
+
 class McStep(C.Structure):
     _fields_ = [("v", C.c_double * 3), ("w", C.c_double * 3), ("n", C.c_double * 3), ("t", C.c_double * 3),
                 ("height", C.c_double),
@@ -54,6 +66,13 @@ class McSums(C.Structure):
 IMU_DTYPE = np.dtype([("d", "<f8"), ("n", "<f8", 3), ("w", "<f8", 3), ("t", "<f8", 3)])
 RESULT_DTYPE = np.dtype([("v", "<f8", 3), ("s", "<f8", 3), ("res", "<f8"), ("rank", "<i4"),
                          ("n_features", "<i4"), ("n_tracked", "<i4")], align=True)
+TRACK_RESULT_DTYPE = np.dtype([("v", "<f8", 3), ("s", "<f8", 3), ("res", "<f8"), ("rank", "<i4"), ("flags", "<i4"),
+                               ("n_prev", "<i4"), ("n_tracked", "<i4"), ("n_kept", "<i4"), ("n_added", "<i4"),
+                               ("n_points", "<i4")], align=True)
+TOPUP_APPEND_MASKED, TOPUP_APPEND, TOPUP_REPLACE = 0, 1, 2
+TOPUP_MODES = {"node": TOPUP_APPEND_MASKED, "exp": TOPUP_APPEND, "module": TOPUP_REPLACE}
+GATE_NONE, GATE_R_GE, GATE_R_LE = 0, 1, 2
+TRACK_SOLVED, TRACK_OVERFLOW = 1, 2
 MCSUMS_DTYPE = np.dtype([("n", "<f8"), ("sum_dv", "<f8", 3), ("sum_dv2", "<f8", 3), ("sum_R", "<f8")])
 
 _lib = None
@@ -94,6 +113,13 @@ _SIGNATURES = {
     "ofb_r_tilde": (i32, [vp, vp, vp, i32, i32, vp, vp, f64, vp, vp]),
     "ofb_feasibility": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "ofb_frame_pairs": (i32, [vp, C.POINTER(PairCfg), i32, vp, vp, i32, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "ofb_tracker_create": (i32, [vp, C.POINTER(TrackerCfg), C.POINTER(vp)]),
+    "ofb_tracker_destroy": (i32, [vp]),
+    "ofb_tracker_reset": (i32, [vp]),
+    "ofb_tracker_capacity": (i32, [vp, C.POINTER(i32)]),
+    "ofb_tracker_set_points": (i32, [vp, vp, vp]),
+    "ofb_tracker_step": (i32, [vp, vp, i32, sz, vp, vp, vp, vp, vp, vp, vp]),
+    "ofb_tracker_render_mask": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ofb_mc_sweep": (i32, [vp, vp, i32, i32, vp, vp, i32, u64, u64, u64, i32, vp, vp, vp]),
     "ofb_mc_feas": (i32, [vp, vp, i32, vp, vp, u64, u64, u64, vp]),
     "ofb_minmax": (i32, [vp, vp, sz, C.POINTER(f64), C.POINTER(f64)]),

@@ -1,0 +1,501 @@
+// tracker.cu -- feature lifecycle around the tracker: the point sets of n_streams camera streams
+// live on the device between frames; one step = ingest -> pyramid -> LK -> status filter + gates -> solve ->
+// top-up detection, with no host round trip between the stages (counts and "needs top-up" flags stay on the device).
+//
+// Replaces the per-frame loops around cv2.calcOpticalFlowPyrLK in the reference:
+//   flight_experiments/evaluate_exp.py:97-120   track, new_pos[status==1], top-up when <= min_feat, solve_lgs
+//   velocity_measurment_node:129-172, 224-260   track + status filter, r_tilde gate, solve, masked top-up
+//   optical_flow_experiments/of_module.py:83-131 re-detect when <= 10 remain, r_tilde gate with `status`
+//   of_library.py:88-92                          static_immobile speed gate
+//
+// Kernels (all tiny next to the pyramid / LK / lambda_min kernels they sit between):
+//   ingest_bgr_kernel        BGR8 -> grey straight into the tracker's level-0 buffer (cv2.cvtColor arithmetic)
+//   track_filter_solve_kernel one CTA per stream: ordered compaction of the surviving points (ballot + block
+//                            scan), the two gates, then the fp64 normal-equation solve on the kept points
+//   mask_fill_kernel / mask_circle_kernel  exclusion mask of the masked top-up, only for streams that need it
+//   topup_append_kernel      appends the first (max_features - count) detected corners (greedy selection has the
+//                            prefix property: the first m corners of a longer run are the run with maxCorners = m)
+#include "common.cuh"
+#include "features.cuh"
+#include "pyrlk.cuh"
+#include "velocity_device.cuh"
+
+struct ofb_tracker {
+    ofb_ctx* ctx = nullptr;
+    ofb_tracker_cfg cfg;
+    int cap = 0;                       // points per stream
+    int pitch_d = 0;                   // level-0 pitch of the tracker's own frame buffers
+    size_t stride_d = 0;
+    DevBuf frames[2];                  // grey level 0 of the previous / current frame (ping-pong)
+    ofb_pyr* pyr[2] = {nullptr, nullptr};
+    int cur = 0;                       // slot the NEXT frame goes to
+    bool have_prev = false;
+    DevBuf pts[2];                     // float2 [S][cap]; pts[pcur] = current point sets
+    int pcur = 0;
+    DevBuf counts;                     // int [3][S]: count, need (top-up flag), kept (count after the gates)
+    DevBuf nxt, status, err, kept_prev, det, vlast, mask, hw, bgr;
+};
+
+namespace {
+
+struct TrackerDev {
+    const float* prev; const float* next; const uint8_t* status;   // [S][cap] LK input / output
+    float* kept_prev; float* kept_next;                             // [S][cap] compacted
+    int* count; int* need; int* kept;
+    double* vlast;                                                  // [S][3]
+    int cap;
+    int variant; double cx, cy, ps, fs;
+    double max_speed, dummy; int gate_mode; double gate_T;
+    int min_solve, min_features, topup_mode, max_features;
+    int have_prev;
+};
+
+struct KeptLoader {
+    const float* prev; const float* next; int n; size_t stride;
+    double cx, cy, ps, fs;
+    __device__ int begin(int) const { return 0; }
+    __device__ int end(int) const { return n; }
+    __device__ bool load(int f, int i, double& px, double& py, double& ux, double& uy) const {
+        size_t o = (size_t)f * stride + i;
+        float nx = next[2 * o], ny = next[2 * o + 1];
+        float dx = nx - prev[2 * o], dy = ny - prev[2 * o + 1];     // fp32 flow, as cv2's float32 arrays (node:136)
+        px = ((double)nx - cx) * ps; py = ((double)ny - cy) * ps;    // node:232-233
+        ux = (double)dx * fs; uy = (double)dy * fs;                  // node:235
+        return true;
+    }
+};
+
+// of.r_tilde (of_library.py:365-386, 5-argument form), feasibility value only
+__device__ __forceinline__ double r_tilde_point(double px, double py, double ux, double uy, const double n3[3],
+                                                const double v[3])
+{
+    // a = -(X x v), b = X x u3 with X = (px, py, 1), u3 = (ux, uy, 0)
+    double a0 = -(py * v[2] - v[1]), a1 = -(v[0] - px * v[2]), a2 = -(px * v[1] - py * v[0]);
+    double b0 = -uy, b1 = ux, b2 = px * uy - py * ux;
+    double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2), nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+    if (nb * na == 0.0) return 1.0;                                   // of_library.py:377-379
+    double r = (a0 * b0 + a1 * b1 + a2 * b2) * (1.0 / nb) / na;
+    if (n3[0] * px + n3[1] * py + n3[2] < 0) r = -r;
+    return r;
+}
+
+__global__ void __launch_bounds__(OFB_SOLVE_THREADS)
+track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, const double* __restrict__ v_prior,
+                          ofb_track_result* __restrict__ out)
+{
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int wtot[OFB_SOLVE_THREADS / 32];
+    const ofb_imu_sample& im = imu[s];
+    const int n = T.count[s];                                         // first frame: seeded points (or none) carry over
+    const size_t base = (size_t)s * T.cap;
+    double vp[3];
+    {
+        const double* src = v_prior ? v_prior + 3 * s : T.vlast + 3 * s;
+        vp[0] = src[0]; vp[1] = src[1]; vp[2] = src[2];
+    }
+    const double n3[3] = {im.n[0], im.n[1], im.n[2]};
+    // static_immobile compares float32 arrays with a Python scalar: the threshold takes the arrays' type
+    const float speed_thr = T.max_speed > 0 ? (float)(T.max_speed / im.d) : 0.f;
+    const float dummy = (float)T.dummy;
+    int kept = 0, tracked = 0;
+    for (int i0 = 0; i0 < n; i0 += OFB_SOLVE_THREADS) {
+        const int i = i0 + tid;
+        bool st = false, keep = false;
+        float px = 0, py = 0, qx = 0, qy = 0;
+        if (i < n) {
+            px = T.prev[2 * (base + i)]; py = T.prev[2 * (base + i) + 1];
+            if (T.have_prev) {
+                st = T.status[base + i] != 0;                        // new_pos[status==1]  evaluate_exp.py:99
+                qx = T.next[2 * (base + i)]; qy = T.next[2 * (base + i) + 1];
+            } else { st = true; qx = px; qy = py; }
+            keep = st;
+            if (keep && T.have_prev && T.max_speed > 0) {                           // of_library.py:88-92
+                const bool speed_ok = fabsf(qx - px) < speed_thr && fabsf(qy - py) < speed_thr;
+                const bool not_dummy = px != dummy && py != dummy;
+                keep = speed_ok && not_dummy;
+            }
+            if (keep && T.have_prev && T.gate_mode != OFB_GATE_NONE) {              // node:238-245, of_module.py:125-131
+                const float dx = qx - px, dy = qy - py;
+                const double r = r_tilde_point(((double)qx - T.cx) * T.ps, ((double)qy - T.cy) * T.ps, (double)dx * T.fs,
+                                               (double)dy * T.fs, n3, vp);
+                keep = T.gate_mode == OFB_GATE_R_GE ? r >= T.gate_T : r <= T.gate_T;
+            }
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+        const unsigned int bst = __ballot_sync(0xffffffffu, st);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        tracked += __popc(bst);                                       // per-warp partial, summed below
+        __syncthreads();
+        int off = kept, tot = 0;
+#pragma unroll
+        for (int k = 0; k < OFB_SOLVE_THREADS / 32; ++k) { if (k < warp) off += wtot[k]; tot += wtot[k]; }
+        if (keep) {
+            const size_t o = base + off + __popc(bal & ((1u << lane) - 1u));
+            T.kept_prev[2 * o] = px; T.kept_prev[2 * o + 1] = py;
+            T.kept_next[2 * o] = qx; T.kept_next[2 * o + 1] = qy;
+        }
+        kept += tot;
+        __syncthreads();
+    }
+    // tracked: every lane of a warp holds its warp's total; sum over warps
+    if (lane == 0) wtot[warp] = tracked;
+    __syncthreads();
+    tracked = 0;
+#pragma unroll
+    for (int k = 0; k < OFB_SOLVE_THREADS / 32; ++k) tracked += wtot[k];
+    __syncthreads();                                                  // kept_* visible to the whole CTA
+    OfbSolveOut o;
+    const bool solve = T.have_prev && kept >= T.min_solve && kept > 0;
+    if (solve) {
+        KeptLoader ld{T.kept_prev, T.kept_next, kept, (size_t)T.cap, T.cx, T.cy, T.ps, T.fs};
+        o = ofb_block_solve(ld, s, T.variant, im.d, im.n, im.w, im.t);
+    }
+    if (tid == 0) {
+        ofb_track_result r;
+        for (int k = 0; k < 3; ++k) { r.v[k] = solve ? o.v[k] : 0.0; r.s[k] = solve ? o.s[k] : 0.0; }
+        r.res = solve ? o.res : 0.0; r.rank = solve ? o.rank : 0;
+        r.flags = solve ? OFB_TRACK_SOLVED : 0;
+        r.n_prev = n; r.n_tracked = tracked; r.n_kept = kept; r.n_added = 0; r.n_points = kept;
+        out[s] = r;
+        if (solve) { T.vlast[3 * s] = o.v[0]; T.vlast[3 * s + 1] = o.v[1]; T.vlast[3 * s + 2] = o.v[2]; }
+        const int need = kept <= T.min_features;
+        T.kept[s] = kept;
+        T.need[s] = need;
+        T.count[s] = (need && T.topup_mode == OFB_TOPUP_REPLACE) ? 0 : kept;    // of_module.py:86 replaces the set
+    }
+}
+
+// (3735 B + 19235 G + 9798 R + 2^14) >> 15, four pixels per thread
+__global__ void ingest_bgr_kernel(const uint8_t* __restrict__ bgr, int w, int h, int pitch, size_t istride,
+                                  uint8_t* __restrict__ gray, int gpitch, size_t gstride, int vec)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= w) return;
+    const uint8_t* p = bgr + (size_t)blockIdx.z * istride + (size_t)y * pitch + 3 * (size_t)x4;
+    uint8_t* g = gray + (size_t)blockIdx.z * gstride + (size_t)y * gpitch + x4;
+    uint8_t b[12];
+    const int npx = min(4, w - x4);
+    if (vec && npx == 4) {
+        const uint32_t* q = (const uint32_t*)p;
+        uint32_t a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b[k] = (a0 >> (8 * k)) & 255; b[4 + k] = (a1 >> (8 * k)) & 255; b[8 + k] = (a2 >> (8 * k)) & 255; }
+    } else {
+        for (int k = 0; k < 3 * npx; ++k) b[k] = p[k];
+    }
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < npx) {
+            const uint32_t v = (3735u * b[3 * k] + 19235u * b[3 * k + 1] + 9798u * b[3 * k + 2] + 16384u) >> 15;
+            o |= v << (8 * k);
+        }
+    if (npx == 4) *(uint32_t*)g = o;                                  // gpitch and gstride are multiples of 16
+    else for (int k = 0; k < npx; ++k) g[k] = (o >> (8 * k)) & 255;
+}
+
+__global__ void mask_fill_kernel(uint8_t* __restrict__ mask, size_t mstride, const int* __restrict__ need)
+{
+    const int s = blockIdx.y;
+    if (need && !need[s]) return;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i < mstride) *(uint4*)(mask + (size_t)s * mstride + i) = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+}
+
+// cv2.circle(mask, (int(x), int(y)), radius, 0, FILLED): clipped union of the midpoint-circle spans; hw[|dy|] is the
+// half width of row cy+dy (computed once on the host from OpenCV's loop). One CTA per point, threads over rows.
+__global__ void mask_circle_kernel(uint8_t* __restrict__ mask, int w, int h, int mpitch, size_t mstride,
+                                   const float* __restrict__ pts, size_t pts_stride, const int* __restrict__ count,
+                                   const int* __restrict__ need, const int* __restrict__ hw, int radius)
+{
+    const int s = blockIdx.y, i = blockIdx.x;
+    if (need && !need[s]) return;
+    if (i >= count[s]) return;
+    const float fx = pts[2 * ((size_t)s * pts_stride + i)], fy = pts[2 * ((size_t)s * pts_stride + i) + 1];
+    const int cx = (int)fx, cy = (int)fy;                             // Python-2 cv2 truncates float coordinates
+    uint8_t* m = mask + (size_t)s * mstride;
+    for (int r = threadIdx.x; r <= 2 * radius; r += blockDim.x) {
+        const int dy = r - radius, y = cy + dy;
+        if (y < 0 || y >= h) continue;
+        const int half = hw[dy < 0 ? -dy : dy];
+        const int x0 = max(cx - half, 0), x1 = min(cx + half, w - 1);
+        for (int x = x0; x <= x1; ++x) m[(size_t)y * mpitch + x] = 0;
+    }
+}
+
+__global__ void topup_append_kernel(TrackerDev T, const FeatImageState* __restrict__ st, const float* __restrict__ det,
+                                    float* __restrict__ pts, ofb_track_result* __restrict__ out)
+{
+    const int s = blockIdx.x;
+    if (!T.need[s]) return;
+    const int ndet = st[s].n_out, cnt = T.count[s];
+    int take = T.topup_mode == OFB_TOPUP_APPEND ? T.max_features : T.max_features - T.kept[s];
+    take = min(take, ndet);
+    take = min(take, T.cap - cnt);
+    if (take < 0) take = 0;
+    const float2* src = (const float2*)det + (size_t)s * T.max_features;
+    float2* dst = (float2*)pts + (size_t)s * T.cap + cnt;
+    for (int i = threadIdx.x; i < take; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+        T.count[s] = cnt + take;
+        out[s].n_added = take;
+        out[s].n_points = cnt + take;
+        if (st[s].overflow) out[s].flags |= OFB_TRACK_OVERFLOW;
+    }
+}
+
+// OpenCV's Circle() (imgproc/drawing.cpp) walks (dx, dy) from (radius, 0) while dx >= dy, filling rows cy+-dy over
+// cx+-dx and rows cy+-dx over cx+-dy; the half width of a row is the widest span that touched it.
+void circle_half_widths(int radius, std::vector<int>& hw)
+{
+    hw.assign((size_t)radius + 1, -1);
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        if (hw[dy] < dx) hw[dy] = dx;
+        if (hw[dx] < dy) hw[dx] = dy;
+        dy++;
+        err += plus;
+        plus += 2;
+        const int m = (err <= 0) - 1;
+        err -= minus & m;
+        dx += m;
+        minus -= m & 2;
+    }
+    for (int r = 0; r <= radius; ++r) if (hw[r] < 0) hw[r] = 0;
+}
+
+int render_mask_device(ofb_ctx* ctx, uint8_t* mask, int w, int h, int mpitch, size_t mstride, int n_streams,
+                       const float* pts, size_t pts_stride, int max_pts, const int* count, const int* need, const int* hw,
+                       int radius)
+{
+    dim3 fg((unsigned int)((mstride / 16 + 255) / 256), n_streams);
+    mask_fill_kernel<<<fg, 256, 0, ctx->stream>>>(mask, mstride, need);
+    OFB_LAUNCH_CHECK(ctx);
+    if (max_pts > 0 && radius >= 0) {
+        dim3 cg(max_pts, n_streams);
+        mask_circle_kernel<<<cg, 64, 0, ctx->stream>>>(mask, w, h, mpitch, mstride, pts, pts_stride, count, need, hw, radius);
+        OFB_LAUNCH_CHECK(ctx);
+    }
+    return OFB_OK;
+}
+
+}  // namespace
+
+extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_tracker** out)
+{
+    OFB_REQUIRE(ctx && cfg && out, "tracker_create: null argument");
+    const ofb_pair_cfg& p = cfg->pair;
+    OFB_REQUIRE(p.width >= 2 && p.height >= 2, "tracker_create: bad image geometry");
+    OFB_REQUIRE(p.max_corners > 0, "tracker_create: max_features (pair.max_corners) must be positive");
+    OFB_REQUIRE(p.max_level >= 0, "tracker_create: max_level must be >= 0");
+    OFB_REQUIRE(p.variant >= 0 && p.variant <= 2, "tracker_create: unknown variant");
+    OFB_REQUIRE(cfg->n_streams >= 1 && cfg->n_streams <= 65535, "tracker_create: n_streams must be in 1..65535");
+    OFB_REQUIRE(cfg->min_features >= 0 && cfg->min_features < p.max_corners,
+                "tracker_create: min_features must be in 0..max_features-1");
+    OFB_REQUIRE(cfg->topup_mode >= 0 && cfg->topup_mode <= 2, "tracker_create: unknown topup_mode");
+    OFB_REQUIRE(cfg->gate_mode >= 0 && cfg->gate_mode <= 2, "tracker_create: unknown gate_mode");
+    OFB_REQUIRE(cfg->mask_radius >= 0 && cfg->mask_radius <= 4096, "tracker_create: mask_radius must be in 0..4096");
+    OFB_REQUIRE(cfg->min_solve >= 0, "tracker_create: min_solve must be >= 0");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    ofb_tracker* t = new ofb_tracker();
+    t->ctx = ctx; t->cfg = *cfg;
+    const int S = cfg->n_streams, K = p.max_corners;
+    t->cap = K + (cfg->topup_mode == OFB_TOPUP_APPEND ? cfg->min_features : 0);
+    t->pitch_d = (p.width + 15) & ~15;
+    t->stride_d = (((size_t)t->pitch_d * p.height) + 255) & ~(size_t)255;
+    int rc = OFB_OK;
+    auto R = [&](DevBuf& b, size_t bytes) { if (rc == OFB_OK) rc = b.reserve(bytes); };
+    R(t->frames[0], t->stride_d * S + 256); R(t->frames[1], t->stride_d * S + 256);
+    const size_t np = (size_t)S * t->cap;
+    R(t->pts[0], sizeof(float) * 2 * np); R(t->pts[1], sizeof(float) * 2 * np);
+    R(t->nxt, sizeof(float) * 2 * np); R(t->kept_prev, sizeof(float) * 2 * np);
+    R(t->status, np); R(t->err, sizeof(float) * np);
+    R(t->counts, sizeof(int) * 3 * S); R(t->det, sizeof(float) * 2 * (size_t)S * K);
+    R(t->vlast, sizeof(double) * 3 * S);
+    if (cfg->topup_mode == OFB_TOPUP_APPEND_MASKED && cfg->mask_radius > 0) {
+        R(t->mask, t->stride_d * S);
+        R(t->hw, sizeof(int) * ((size_t)cfg->mask_radius + 1));
+    }
+    if (rc != OFB_OK) { ofb_tracker_destroy(t); return rc; }
+    if (t->hw.p) {
+        std::vector<int> hw;
+        circle_half_widths(cfg->mask_radius, hw);
+        OFB_CUDA(cudaMemcpyAsync(t->hw.p, hw.data(), sizeof(int) * hw.size(), cudaMemcpyHostToDevice, ctx->stream));
+        OFB_CUDA(cudaStreamSynchronize(ctx->stream));                 // hw is a local
+    }
+    OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * S, ctx->stream));
+    OFB_CUDA(cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * S, ctx->stream));
+    *out = t;
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_destroy(ofb_tracker* t)
+{
+    OFB_REQUIRE(t, "tracker_destroy: null tracker");
+    if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (t->pyr[i]) { cudaFree(t->pyr[i]->base); delete t->pyr[i]; }
+        t->frames[i].release(); t->pts[i].release();
+    }
+    DevBuf* bufs[] = {&t->counts, &t->nxt, &t->status, &t->err, &t->kept_prev, &t->det, &t->vlast, &t->mask, &t->hw, &t->bgr};
+    for (DevBuf* b : bufs) b->release();
+    delete t;
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_reset(ofb_tracker* t)
+{
+    OFB_REQUIRE(t, "tracker_reset: null tracker");
+    OFB_CUDA(cudaSetDevice(t->ctx->device));
+    t->have_prev = false;
+    OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * t->cfg.n_streams, t->ctx->stream));
+    OFB_CUDA(cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * t->cfg.n_streams, t->ctx->stream));
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_capacity(const ofb_tracker* t, int* capacity_out)
+{
+    OFB_REQUIRE(t && capacity_out, "tracker_capacity: null argument");
+    *capacity_out = t->cap;
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_set_points(ofb_tracker* t, const float* pts, const int* counts)
+{
+    OFB_REQUIRE(t && pts && counts, "tracker_set_points: null argument");
+    ofb_ctx* ctx = t->ctx;
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const int S = t->cfg.n_streams;
+    if (!ofb_is_device_ptr(counts))
+        for (int s = 0; s < S; ++s)
+            OFB_REQUIRE(counts[s] >= 0 && counts[s] <= t->cap, "tracker_set_points: counts[%d] = %d outside 0..%d", s, counts[s], t->cap);
+    OFB_CUDA(cudaMemcpyAsync(t->pts[t->pcur].p, pts, sizeof(float) * 2 * (size_t)S * t->cap, cudaMemcpyDefault, ctx->stream));
+    OFB_CUDA(cudaMemcpyAsync(t->counts.p, counts, sizeof(int) * S, cudaMemcpyDefault, ctx->stream));
+    OFB_CUDA(cudaStreamSynchronize(ctx->stream));                     // the caller's buffers are free on return
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch, size_t image_stride,
+                                const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
+                                float* pts_out, int* n_out, float* kept_prev, float* kept_next)
+{
+    OFB_REQUIRE(t && frames && imu && results, "tracker_step: null argument");
+    ofb_ctx* ctx = t->ctx;
+    const ofb_tracker_cfg& cfg = t->cfg;
+    const ofb_pair_cfg& pc = cfg.pair;
+    const int S = cfg.n_streams, w = pc.width, h = pc.height, K = pc.max_corners, cap = t->cap;
+    const int bpp = cfg.bgr_input ? 3 : 1;
+    OFB_REQUIRE(pitch >= bpp * w, "tracker_step: pitch smaller than a row");
+    OFB_REQUIRE(S == 1 || image_stride >= (size_t)pitch * (h - 1) + (size_t)bpp * w, "tracker_step: image_stride too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const size_t np = (size_t)S * cap;
+    OutStage o[2];
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT3, results, sizeof(ofb_track_result) * S, &o[0]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT2, n_out, sizeof(int) * S, &o[1]));
+    const void *dimu, *dvp = nullptr;
+    OFB_TRY(ofb_stage_in(ctx, SC_IN3, imu, sizeof(ofb_imu_sample) * S, &dimu));
+    if (v_prior) OFB_TRY(ofb_stage_in(ctx, SC_IN4, v_prior, sizeof(double) * 3 * S, &dvp));
+    // 1. ingest: the tracker keeps its own copy of the frame (it is "old_image" of the next step)
+    uint8_t* f = t->frames[t->cur].as<uint8_t>();
+    if (cfg.bgr_input) {
+        const uint8_t* src = frames; int spitch = pitch; size_t sstride = image_stride;
+        if (!ofb_is_device_ptr(frames)) {
+            spitch = (3 * w + 3) & ~3; sstride = ((size_t)spitch * h + 15) & ~(size_t)15;
+            OFB_TRY(t->bgr.reserve(sstride * S));
+            for (int s = 0; s < S; ++s)
+                OFB_CUDA(cudaMemcpy2DAsync(t->bgr.as<uint8_t>() + (size_t)s * sstride, spitch, frames + (size_t)s * image_stride,
+                                           pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+            src = t->bgr.as<uint8_t>();
+        }
+        const int vec = ((uintptr_t)src % 4 == 0 && spitch % 4 == 0 && sstride % 4 == 0) ? 1 : 0;
+        dim3 grid(ofb_div_up(ofb_div_up(w, 4), 128), h, S);
+        ingest_bgr_kernel<<<grid, 128, 0, ctx->stream>>>(src, w, h, spitch, sstride, f, t->pitch_d, t->stride_d, vec);
+        OFB_LAUNCH_CHECK(ctx);
+    } else if (pitch == t->pitch_d && (S == 1 || image_stride == t->stride_d)) {
+        OFB_CUDA(cudaMemcpyAsync(f, frames, t->stride_d * (size_t)(S - 1) + (size_t)pitch * (h - 1) + w, cudaMemcpyDefault, ctx->stream));
+    } else {
+        for (int s = 0; s < S; ++s)
+            OFB_CUDA(cudaMemcpy2DAsync(f + (size_t)s * t->stride_d, t->pitch_d, frames + (size_t)s * image_stride, pitch, w, h,
+                                       cudaMemcpyDefault, ctx->stream));
+    }
+    OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, t->pitch_d, t->stride_d, S, S, pc.max_level, true));
+    int* count = t->counts.as<int>();
+    int* need = count + S;
+    int* keptn = count + 2 * S;
+    float* P = t->pts[t->pcur].as<float>();
+    float* Pn = t->pts[t->pcur ^ 1].as<float>();
+    TrackerDev T;
+    T.prev = P; T.next = t->nxt.as<float>(); T.status = t->status.as<uint8_t>();
+    T.kept_prev = t->kept_prev.as<float>(); T.kept_next = Pn;
+    T.count = count; T.need = need; T.kept = keptn; T.vlast = t->vlast.as<double>();
+    T.cap = cap; T.variant = pc.variant; T.cx = pc.cx; T.cy = pc.cy; T.ps = pc.pos_scale; T.fs = pc.flow_scale;
+    T.max_speed = cfg.max_speed; T.dummy = cfg.dummy_value; T.gate_mode = cfg.gate_mode; T.gate_T = cfg.gate_T;
+    T.min_solve = cfg.min_solve; T.min_features = cfg.min_features; T.topup_mode = cfg.topup_mode; T.max_features = K;
+    T.have_prev = t->have_prev ? 1 : 0;
+    // 2. track the stream's points from the kept frame into the new one
+    if (t->have_prev)
+        OFB_TRY(ofb_lk_device(ctx, t->pyr[t->cur ^ 1], 0, 1, t->pyr[t->cur], 0, 1, S, P, count, 1, cap, (size_t)cap, pc.win_w,
+                              pc.win_h, pc.max_level, pc.max_count, pc.eps, 0, pc.min_eig_thr, t->nxt.as<float>(),
+                              t->status.as<uint8_t>(), t->err.as<float>()));
+    // 3.+4. status filter, gates, solve; the compacted new positions become the point set (Pn)
+    track_filter_solve_kernel<<<S, OFB_SOLVE_THREADS, 0, ctx->stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
+                                                                        (ofb_track_result*)o[0].dev);
+    OFB_LAUNCH_CHECK(ctx);
+    bool host_out = false;
+    auto copy_out = [&](float* dst, const float* src) -> int {
+        if (!dst) return OFB_OK;
+        OFB_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * 2 * np, cudaMemcpyDefault, ctx->stream));
+        if (!ofb_is_device_ptr(dst)) host_out = true;
+        return OFB_OK;
+    };
+    OFB_TRY(copy_out(kept_prev, t->kept_prev.as<float>()));
+    OFB_TRY(copy_out(kept_next, Pn));                                 // the head of the new point set, before any top-up
+    // 5. top-up on the current frame; streams that do not need it are skipped inside the kernels (no host sync)
+    const uint8_t* mask = nullptr;
+    if (cfg.topup_mode == OFB_TOPUP_APPEND_MASKED && cfg.mask_radius > 0) {
+        OFB_TRY(render_mask_device(ctx, t->mask.as<uint8_t>(), w, h, t->pitch_d, t->stride_d, S, Pn, (size_t)cap, cap, count, need,
+                                   t->hw.as<int>(), cfg.mask_radius));
+        mask = t->mask.as<uint8_t>();
+    }
+    FeatImageState* st = nullptr;
+    const unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
+    ctx->feat_active = need;
+    int fr = ofb_features_device(ctx, f, w, h, t->pitch_d, t->stride_d, S, mask, t->pitch_d, t->stride_d, K, pc.quality,
+                                 pc.min_distance, pc.block_size, cand_cap, t->det.as<float>(), (size_t)2 * K, K, &st);
+    ctx->feat_active = nullptr;
+    OFB_TRY(fr);
+    topup_append_kernel<<<S, 128, 0, ctx->stream>>>(T, st, t->det.as<float>(), Pn, (ofb_track_result*)o[0].dev);
+    OFB_LAUNCH_CHECK(ctx);
+    if (o[1].dev) OFB_CUDA(cudaMemcpyAsync(o[1].dev, count, sizeof(int) * S, cudaMemcpyDeviceToDevice, ctx->stream));
+    OFB_TRY(copy_out(pts_out, Pn));
+    t->pcur ^= 1;
+    t->cur ^= 1;
+    t->have_prev = true;
+    int rc = ofb_finish_out(ctx, o, 2);
+    if (rc == OFB_OK && host_out) OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+extern "C" int ofb_tracker_render_mask(ofb_ctx* ctx, const float* pts, int n, int radius, int w, int h, uint8_t* mask_out)
+{
+    OFB_REQUIRE(ctx && mask_out && (pts || n == 0), "tracker_render_mask: null argument");
+    OFB_REQUIRE(w > 0 && h > 0 && n >= 0 && radius >= 0 && radius <= 4096, "tracker_render_mask: bad arguments");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const int mpitch = (w + 15) & ~15;
+    const size_t mstride = ((size_t)mpitch * h + 255) & ~(size_t)255;
+    OFB_TRY(ctx->scratch[SC_TMP0].reserve(mstride));
+    OFB_TRY(ctx->scratch[SC_TMP1].reserve(sizeof(int) * ((size_t)radius + 2)));
+    std::vector<int> hw;
+    circle_half_widths(radius, hw);
+    hw.push_back(n);                                                  // the count rides behind the table
+    OFB_CUDA(cudaMemcpyAsync(ctx->scratch[SC_TMP1].p, hw.data(), sizeof(int) * hw.size(), cudaMemcpyHostToDevice, ctx->stream));
+    OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const void* dpts = nullptr;
+    OFB_TRY(ofb_stage_in(ctx, SC_IN0, pts, sizeof(float) * 2 * (size_t)n, &dpts));
+    const int* dhw = ctx->scratch[SC_TMP1].as<int>();
+    OFB_TRY(render_mask_device(ctx, ctx->scratch[SC_TMP0].as<uint8_t>(), w, h, mpitch, mstride, 1, (const float*)dpts, (size_t)n, n,
+                               dhw + radius + 1, nullptr, dhw, radius));
+    OFB_CUDA(cudaMemcpy2DAsync(mask_out, w, ctx->scratch[SC_TMP0].p, mpitch, w, h, cudaMemcpyDefault, ctx->stream));
+    OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OFB_OK;
+}

@@ -1,0 +1,146 @@
+"""Feature lifecycle around the tracker, device resident (include/ofb200.h `ofb_tracker_*`).
+
+`StreamTracker.step(frame, imu)` is one iteration of the reference's per-frame loops
+(flight_experiments/evaluate_exp.py:77-120, velocity_measurment_node:110-172 + 224-260,
+optical_flow_experiments/of_module.py:78-147): grey conversion, calcOpticalFlowPyrLK from the previous frame,
+`new_pos[status==1]`, the optional `of.static_immobile` / `of.r_tilde` gates, `solve_lgs`, and a
+goodFeaturesToTrack top-up when the features run low. The point sets never leave the GPU; only the small
+per-stream result record (velocity, counts) comes back.
+
+There is no CPU path: everything runs in libofb200.so (csrc/tracker.cu)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .vision import make_pair_cfg
+
+
+class StreamTracker:
+    """n_streams camera streams advancing in lockstep, one frame each per `step`.
+
+    feature_params / lk_params take the reference's dictionaries verbatim, e.g.
+    dict(qualityLevel=0.7, minDistance=10, blockSize=12) (node:96-102) and
+    dict(winSize=(15,15), maxLevel=3, criteria=(3, 20, 0.03)) (node:105-107).
+    topup: "exp"  -> evaluate_exp.py:105-107 (unmasked, maxCorners=max_features, appended),
+           "node" -> node:157-172 (circles of mask_radius around surviving points, maxCorners=max_features-count),
+           "module" -> of_module.py:83-86 (the set is replaced).
+    gate: None, ("ge", T) (of_module.py:129) or ("le", T) (node:240-245) on of.r_tilde(x, u, n, v_prior, d).
+    max_speed > 0 enables of.static_immobile(new, old, max_speed, d, dummy_value)."""
+
+    def __init__(self, width, height, max_features=100, min_features=20, n_streams=1, feature_params=None,
+                 lk_params=None, topup="exp", mask_radius=30, bgr=False, variant="exp", principal=None,
+                 scaling=1.0, flow_scaling=None, max_speed=0.0, dummy_value=float("nan"), gate=None, min_solve=3,
+                 min_eig_thr=1e-4, ctx=None):
+        fp = dict(qualityLevel=0.01, minDistance=10, blockSize=7)
+        fp.update(feature_params or {})
+        lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+        lk.update(lk_params or {})
+        self.ctx = ctx or _lib.default_context()
+        cfg = _lib.TrackerCfg()
+        cfg.pair = make_pair_cfg(width, height, max_features, quality=fp["qualityLevel"], min_distance=fp["minDistance"],
+                                 block_size=fp["blockSize"], win=lk["winSize"], max_level=lk["maxLevel"],
+                                 criteria=lk["criteria"], min_eig_thr=min_eig_thr, variant=variant, principal=principal,
+                                 pos_scale=scaling, flow_scale=scaling if flow_scaling is None else flow_scaling)
+        cfg.n_streams = int(n_streams)
+        cfg.min_features = int(min_features)
+        cfg.topup_mode = _lib.TOPUP_MODES[topup]
+        cfg.mask_radius = int(mask_radius)
+        cfg.bgr_input = 1 if bgr else 0
+        cfg.max_speed = float(max_speed)
+        cfg.dummy_value = float(dummy_value)
+        if gate is None:
+            cfg.gate_mode, cfg.gate_T = _lib.GATE_NONE, 0.0
+        else:
+            cfg.gate_mode = {"ge": _lib.GATE_R_GE, "le": _lib.GATE_R_LE}[gate[0]]
+            cfg.gate_T = float(gate[1])
+        cfg.min_solve = int(min_solve)
+        self.cfg = cfg
+        self.n_streams, self.width, self.height, self.bgr = int(n_streams), int(width), int(height), bool(bgr)
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.ofb_tracker_create(self.ctx.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+        cap = C.c_int()
+        _lib.check(self.ctx.lib.ofb_tracker_capacity(self.h, C.byref(cap)))
+        self.capacity = cap.value
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.ofb_tracker_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _lib.check(self.ctx.lib.ofb_tracker_reset(self.h))
+
+    def set_points(self, points):
+        """points: one (N,2)/(N,1,2) array per stream (or a single array when n_streams == 1)."""
+        if self.n_streams == 1 and not isinstance(points, (list, tuple)):
+            points = [points]
+        if len(points) != self.n_streams:
+            raise ValueError("one point array per stream is required")
+        buf = np.zeros((self.n_streams, self.capacity, 2), np.float32)
+        cnt = np.zeros(self.n_streams, np.int32)
+        for s, p in enumerate(points):
+            p = np.asarray(p, dtype=np.float32).reshape(-1, 2)
+            if len(p) > self.capacity:
+                raise ValueError("stream %d: %d points exceed the capacity %d" % (s, len(p), self.capacity))
+            buf[s, :len(p)] = p
+            cnt[s] = len(p)
+        _lib.check(self.ctx.lib.ofb_tracker_set_points(self.h, _lib.ptr(buf), _lib.ptr(cnt)))
+
+    def step(self, frames, imu, v_prior=None, want_points=False, want_kept=False):
+        """frames: (H,W) / (S,H,W) uint8 (or (...,3) BGR when bgr=True), NumPy or CUDA tensor; imu: _lib.IMU_DTYPE
+        (S,). Returns the _lib.TRACK_RESULT_DTYPE records (S,); with want_points additionally the list of (N,1,2)
+        float32 point sets after the step; with want_kept the lists of (old, new) positions the solve used."""
+        S, h, w = self.n_streams, self.height, self.width
+        shape = tuple(frames.shape)
+        tail = (h, w, 3) if self.bgr else (h, w)
+        if shape == tail:
+            shape = (1,) + shape
+        if shape != (S,) + tail:
+            raise ValueError("frames must have shape %r, got %r" % ((S,) + tail, tuple(frames.shape)))
+        if isinstance(frames, np.ndarray):
+            frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        elif not frames.is_contiguous():
+            frames = frames.contiguous()
+        bpp = 3 if self.bgr else 1
+        imu = np.ascontiguousarray(imu, dtype=_lib.IMU_DTYPE).reshape(-1)
+        if len(imu) != S:
+            raise ValueError("one IMU sample per stream is required")
+        if v_prior is not None:
+            v_prior = np.ascontiguousarray(v_prior, dtype=np.float64).reshape(S, 3)
+        res = np.zeros(S, _lib.TRACK_RESULT_DTYPE)
+        pts = cnt = kp = kn = None
+        if want_points:
+            pts = np.zeros((S, self.capacity, 2), np.float32)
+            cnt = np.zeros(S, np.int32)
+        if want_kept:
+            kp = np.zeros((S, self.capacity, 2), np.float32)
+            kn = np.zeros((S, self.capacity, 2), np.float32)
+        _lib.check(self.ctx.lib.ofb_tracker_step(self.h, _lib.ptr(frames), bpp * w, bpp * w * h, _lib.ptr(imu),
+                                                 _lib.ptr(v_prior), _lib.ptr(res), _lib.ptr(pts), _lib.ptr(cnt),
+                                                 _lib.ptr(kp), _lib.ptr(kn)))
+        out = [res]
+        if want_points:
+            out.append([pts[s, :cnt[s]].reshape(-1, 1, 2).copy() for s in range(S)])
+        if want_kept:
+            out.append([kp[s, :res["n_kept"][s]].copy() for s in range(S)])
+            out.append([kn[s, :res["n_kept"][s]].copy() for s in range(S)])
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+def exclusion_mask(points, radius, width, height, ctx=None):
+    """The mask of the masked top-up (node:159-161): ones with cv2.circle(mask, (int(x), int(y)), radius, 0, FILLED)
+    at every point. Returns (H,W) uint8."""
+    ctx = ctx or _lib.default_context()
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float32).reshape(-1, 2))
+    m = np.zeros((int(height), int(width)), np.uint8)
+    _lib.check(ctx.lib.ofb_tracker_render_mask(ctx.h, _lib.ptr(p) if len(p) else None, len(p), int(radius), int(width),
+                                               int(height), _lib.ptr(m)))
+    return m

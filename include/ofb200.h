@@ -186,6 +186,81 @@ int ofb_frame_pairs(ofb_ctx* ctx, const ofb_pair_cfg* cfg, int n_pairs,
                     const ofb_imu_sample* imu, const float* pts_in, const int* n_in,
                     ofb_pair_result* results, float* prev_pts, float* next_pts, uint8_t* status);
 
+/* ---- feature lifecycle around the tracker: the point set of every camera stream stays on the
+ *      device between frames. One step does what the reference's per-frame loops do around the tracker
+ *      (flight_experiments/evaluate_exp.py:97-120, velocity_measurment_node:129-172 and 224-260,
+ *      optical_flow_experiments/of_module.py:83-131):
+ *        1. (optional) BGR -> grey of the new frame (node:113), Gaussian pyramid of the new frame only;
+ *        2. calcOpticalFlowPyrLK from the kept previous frame at the stream's points (evaluate_exp.py:98);
+ *        3. new_pos[status==1], order preserved (evaluate_exp.py:99, node:134-136), then the optional gates:
+ *           of.static_immobile (of_library.py:88-92: |new-old| < maxspeed/distance per component and
+ *           old != dummy_value) and the r_tilde threshold (node:238-245 keeps r <= T, of_module.py:125-131
+ *           keeps r >= T); points that fail are dropped from the set (node:245);
+ *        4. px -> metric and solve_lgs on the kept points when at least min_solve remain (node:247-250);
+ *        5. top-up when count <= min_features (node:157, evaluate_exp.py:105, of_module.py:83):
+ *           goodFeaturesToTrack on the CURRENT frame, see OFB_TOPUP_*.
+ *      The first step (no previous frame) only detects (evaluate_exp.py:66, of_module.py:44).
+ *      n_streams streams advance in lockstep, one frame each per step (the fleet configuration). */
+#define OFB_TOPUP_APPEND_MASKED 0  /* node:157-172: mask = ones with cv2.circle(mask,(int)p,mask_radius,0,FILLED) at every
+                                      surviving point, maxCorners = max_features - count, appended */
+#define OFB_TOPUP_APPEND        1  /* evaluate_exp.py:105-107: no mask, maxCorners = max_features, appended
+                                      (capacity max_features + min_features) */
+#define OFB_TOPUP_REPLACE       2  /* of_module.py:83-86: the set is replaced by maxCorners = max_features - count */
+#define OFB_GATE_NONE 0
+#define OFB_GATE_R_GE 1            /* keep r_tilde >= gate_T   (of_module.py:129) */
+#define OFB_GATE_R_LE 2            /* keep r_tilde <= gate_T   (node:240-245) */
+#define OFB_TRACK_SOLVED   1       /* ofb_track_result.flags: a velocity was solved this step */
+#define OFB_TRACK_OVERFLOW 2       /* detector candidate buffer overflowed during the top-up */
+typedef struct ofb_tracker ofb_tracker;
+
+typedef struct {
+    ofb_pair_cfg pair;       /* geometry, detector, LK and solve parameters; max_corners = max_features
+                                (node:95 max_feat); `detect` is ignored */
+    int    n_streams;        /* >= 1 */
+    int    min_features;     /* top up when count <= min_features; must be < max_features */
+    int    topup_mode;       /* OFB_TOPUP_* */
+    int    mask_radius;      /* OFB_TOPUP_APPEND_MASKED: circle radius in px (30 at node:161); 0 = no mask */
+    int    bgr_input;        /* 1: frames are BGR8, 3 bytes per pixel (pitch >= 3*width) */
+    double max_speed;        /* > 0 enables of.static_immobile(new, old, max_speed, d, dummy_value) */
+    double dummy_value;
+    int    gate_mode;        /* OFB_GATE_* on of.r_tilde(x, u, n, v_prior, d) */
+    double gate_T;
+    int    min_solve;        /* solve only when at least this many points are kept (3 at node:247) */
+} ofb_tracker_cfg;
+
+typedef struct {
+    double v[3];             /* solve_lgs velocity (zeros unless flags & OFB_TRACK_SOLVED) */
+    double s[3];
+    double res;
+    int    rank;
+    int    flags;
+    int    n_prev;           /* points tracked from (count before the step) */
+    int    n_tracked;        /* status == 1 */
+    int    n_kept;           /* after the gates = points the solve used */
+    int    n_added;          /* appended by the top-up */
+    int    n_points;         /* count after the step */
+} ofb_track_result;
+
+int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_tracker** out);
+int ofb_tracker_destroy(ofb_tracker* trk);
+/* forget the previous frame and all points: the next step detects */
+int ofb_tracker_reset(ofb_tracker* trk);
+/* points per stream the tracker can hold (pts arrays are n_streams x capacity x 2 float32) */
+int ofb_tracker_capacity(const ofb_tracker* trk, int* capacity_out);
+/* replace the point sets (host or device): pts n_streams x capacity x 2, counts[n_streams] */
+int ofb_tracker_set_points(ofb_tracker* trk, const float* pts, const int* counts);
+/* frames: n_streams images (grey u8, or BGR8 when bgr_input), image i at frames + i*image_stride, host or
+ * device; imu: one sample per stream; v_prior: n_streams x 3 prior velocity for the r_tilde gate (NULL = the
+ * stream's last solved velocity, zeros before the first solve). Outputs (host or device; optional ones may be
+ * NULL): results[n_streams]; pts_out n_streams x capacity x 2 and n_out[n_streams] = point sets after the step;
+ * kept_prev / kept_next n_streams x capacity x 2 = the (old, new) positions the solve used (first n_kept). */
+int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t image_stride,
+                     const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
+                     float* pts_out, int* n_out, float* kept_prev, float* kept_next);
+/* the exclusion mask OFB_TOPUP_APPEND_MASKED would use for `n` points (n x 2 float32): mask_out h x w u8
+ * (1 = allowed, 0 = inside a circle). Exposed for parity tests against cv2.circle. */
+int ofb_tracker_render_mask(ofb_ctx* ctx, const float* pts, int n, int radius, int w, int h, uint8_t* mask_out);
+
 /* ---- stage 5: Monte-Carlo error propagation. Replaces of_simulation (simulation.py:36-66),
  *      feas_simulation (simulation.py:70-104) and the per-step np.mean/np.std of the sweep
  *      drivers (e.g. simulation.py:183-202). One ofb_mc_step = one call of of_simulation. */

@@ -1,0 +1,253 @@
+"""GPU parity of the device-resident feature lifecycle (ofb_tracker_*, csrc/tracker.cu) through the C ABI against
+oracle/tracker_oracle.py and the cv2-made golden fixture (tests/golden/tracker_golden.npz). Tolerances: counts and
+appended corners exact (documented float ties are resolved on the GPU's own lambda_min map), tracked positions
+within 2e-4 px for 80 % of the points and 0.05 px for all (north star: 0.05 px), velocities within 1e-9 of the fp64
+NumPy solve on the same kept points (north star: 1e-4 relative)."""
+import os
+
+import numpy as np
+import pytest
+
+import tracker_cases as tc
+from conftest import GOLDEN
+from oracle import image_oracle as io
+from oracle import tracker_oracle
+from oracle import velocity_oracle as vo
+from test_oracle_tracker import LK_TOL, close_positions, teacher_from_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "tracker_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def ofb200():
+    import ofb200
+    return ofb200
+
+
+def imu_records(ofb200, samples):
+    a = np.zeros(len(samples), ofb200._lib.IMU_DTYPE)
+    for i, s in enumerate(samples):
+        a["d"][i], a["n"][i], a["w"][i], a["t"][i] = s["d"], s["n"], s["w"], s["t"]
+    return a
+
+
+def priors(samples):
+    if samples[0]["v_prior"] is None:
+        return None
+    return np.stack([s["v_prior"] for s in samples])
+
+
+def same_record(a, b):
+    """field-wise equality of two result records (the struct's tail padding is not defined)"""
+    return all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+
+
+def make_gpu_tracker(ofb200, ctx, kw, n_streams):
+    return ofb200.StreamTracker(tc.W, tc.H, n_streams=n_streams, ctx=ctx, **kw)
+
+
+def test_exclusion_mask_equals_cv2_circle(ofb200, ctx, g):
+    for m, meta in zip(g["circle_masks"], g["circle_meta"]):
+        radius, pts = int(meta[0]), meta[1:].reshape(-1, 2)
+        got = ofb200.exclusion_mask(pts, radius, m.shape[1], m.shape[0], ctx=ctx)
+        assert np.array_equal(got, m), "radius %d" % radius
+    assert ofb200.exclusion_mask(np.zeros((0, 2)), 5, 33, 17, ctx=ctx).min() == 1
+
+
+def check_topup(ofb200, ctx, kw, gray, kept_next, added, tag):
+    """Appended corners = OpenCV's selection rule applied exactly to the GPU's own lambda_min map (tie contract of
+    tests/test_gpu_vision.py), under the same mask / maxCorners the reference's loop would use."""
+    fp = kw["feature_params"]
+    K, mode = kw["max_features"], kw["topup"]
+    mask = None
+    if mode == "node" and kw.get("mask_radius", 30) > 0:
+        mask = tracker_oracle.exclusion_mask(kept_next, kw.get("mask_radius", 30), tc.W, tc.H)
+    mc = K if mode == "exp" else K - len(kept_next)
+    eig = ofb200.cornerMinEigenVal(gray, fp["blockSize"], ctx=ctx)
+    exp = io.select_features(eig, mc, fp["qualityLevel"], fp["minDistance"], mask)
+    exp = np.zeros((0, 2), np.float32) if exp is None else exp.reshape(-1, 2)
+    assert np.array_equal(added, exp), tag + ": top-up differs from the selection rule on the GPU's own map"
+
+
+@pytest.mark.parametrize("name", sorted(tc.SCENARIOS))
+def test_tracker_steps_vs_golden_and_oracle(ofb200, ctx, g, name):
+    """Teacher-forced: before every step the point sets are set to the golden ones, so each step is compared with
+    the cv2 + reference result on identical inputs. All streams of the scenario advance in one tracker."""
+    frames, imus, kw = tc.build(name)
+    S, T = len(frames), len(frames[0])
+    teacher = teacher_from_golden(g, name)
+    trk = make_gpu_tracker(ofb200, ctx, kw, S)
+    try:
+        identical_topups = total_topups = 0
+        for k in range(T):
+            if k > 0:
+                trk.set_points([teacher[s][k] for s in range(S)])
+            fr = np.stack([frames[s][k] for s in range(S)])
+            samples = [imus[s][k] for s in range(S)]
+            res, pts, kp, kn = trk.step(fr, imu_records(ofb200, samples), v_prior=priors(samples), want_points=True,
+                                        want_kept=True)
+            for s in range(S):
+                tag = "%s stream %d step %d" % (name, s, k)
+                for key in ("n_prev", "n_tracked", "n_kept", "n_added", "n_points"):
+                    assert res[key][s] == g["%s_%s" % (name, key)][s, k], "%s: %s" % (tag, key)
+                nk, npts, na = int(res["n_kept"][s]), int(res["n_points"][s]), int(res["n_added"][s])
+                assert len(pts[s]) == npts
+                assert close_positions(kn[s], g[name + "_kept_next"][s, k, :nk], LK_TOL), tag
+                assert np.array_equal(kp[s], g[name + "_kept_prev"][s, k, :nk]), tag
+                P = pts[s].reshape(-1, 2)
+                if kw["topup"] != "module" or na == 0:
+                    assert np.array_equal(P[:npts - na], kn[s]), tag + ": kept points lead the new set"
+                if na:
+                    total_topups += 1
+                    gray = io.bgr2gray(frames[s][k]) if kw["bgr"] else frames[s][k]
+                    added = P[npts - na:]
+                    if np.array_equal(added, g[name + "_pts"][s, k, npts - na:npts]):
+                        identical_topups += 1
+                    check_topup(ofb200, ctx, kw, gray, kn[s], added, tag)
+                solved = bool(res["flags"][s] & ofb200._lib.TRACK_SOLVED)
+                assert solved == bool(g[name + "_solved"][s, k]), tag
+                if solved:
+                    gv = g[name + "_v"][s, k]
+                    assert np.abs(res["v"][s] - gv).max() <= 2e-3 * np.abs(gv).max(), tag + ": velocity vs cv2 golden"
+                    c = np.array([kw.get("principal") or vo.pix_trans((tc.W, tc.H))], np.float64)
+                    x = (kn[s].astype(np.float64) - c) * kw["scaling"]
+                    u = (kn[s] - kp[s]).astype(np.float64) * kw["scaling"]
+                    sm = samples[s]
+                    v, r_, rank, sv = vo.solve_lgs(x, u, sm["d"], sm["n"], sm["w"], None if kw["variant"] == "node" else sm["t"],
+                                                   kw["variant"])
+                    assert np.abs(res["v"][s] - v).max() <= 1e-9 * max(np.abs(v).max(), 1.0), tag + ": velocity vs fp64 solve"
+                    assert int(res["rank"][s]) == int(rank), tag
+                    assert np.allclose(res["s"][s], sv, rtol=1e-7), tag
+                    if np.size(r_):
+                        assert abs(res["res"][s] - float(r_[0])) <= 1e-7 * max(float(r_[0]), 1e-12), tag
+        assert total_topups >= 3
+        assert identical_topups >= total_topups - 1, "more than one top-up needed the tie rule"
+    finally:
+        trk.close()
+
+
+def run_free(ofb200, ctx, kw, frames, imus, device_frames=False):
+    import torch
+    S, T = len(frames), len(frames[0])
+    trk = make_gpu_tracker(ofb200, ctx, kw, S)
+    out = []
+    try:
+        for k in range(T):
+            fr = np.stack([frames[s][k] for s in range(S)])
+            if device_frames:
+                fr = torch.from_numpy(fr).cuda()
+            samples = [imus[s][k] for s in range(S)]
+            res, pts = trk.step(fr, imu_records(ofb200, samples), v_prior=priors(samples), want_points=True)
+            out.append((res.copy(), pts))
+    finally:
+        trk.close()
+    return out
+
+
+def test_free_running_device_resident_chain(ofb200, ctx, g):
+    """No teacher: the point set lives on the device for 8 frames; counts equal the cv2 chain and 80 % of the points
+    stay within 0.05 px of it (points tracked into the occluding noise block wander chaotically)."""
+    name = "exp"
+    frames, imus, kw = tc.build(name)
+    out = run_free(ofb200, ctx, kw, frames, imus)
+    for k, (res, pts) in enumerate(out):
+        for key in ("n_prev", "n_tracked", "n_kept", "n_added", "n_points"):
+            assert res[key][0] == g["%s_%s" % (name, key)][0, k], "step %d: %s" % (k, key)
+        assert close_positions(pts[0].reshape(-1, 2), g[name + "_pts"][0, k, :len(pts[0])], 0.05, worst=float("inf"))
+        if res["flags"][0] & 1:
+            gv = g[name + "_v"][0, k]
+            assert np.abs(res["v"][0] - gv).max() <= 0.05 * np.abs(gv).max()
+
+
+@pytest.mark.parametrize("name", ["module", "node"])
+def test_streams_are_independent_and_device_frames_match(ofb200, ctx, name):
+    """A multi-stream tracker gives every stream exactly what a single-stream tracker gives it, from host frames
+    and from device-resident frames (bit-identical: same kernels, same per-stream data)."""
+    frames, imus, kw = tc.build(name)
+    if len(frames) == 1:        # make it a 3-stream fleet: the stream, a shifted copy and the stream again
+        frames = [frames[0], frames[0][::-1].copy(), frames[0]]
+        imus = [imus[0], imus[0][::-1], imus[0]]
+    both = run_free(ofb200, ctx, kw, frames, imus)
+    dev = run_free(ofb200, ctx, kw, frames, imus, device_frames=True)
+    for s in range(len(frames)):
+        single = run_free(ofb200, ctx, kw, [frames[s]], [imus[s]])
+        for k in range(len(frames[0])):
+            for other in (both, dev):
+                assert same_record(other[k][0][s], single[k][0][0]), "stream %d step %d" % (s, k)
+                assert np.array_equal(other[k][1][s], single[k][1][0])
+
+
+def test_seeded_points_and_reset(ofb200, ctx):
+    """set_points before the first frame (node:123-128 seeds test points): the first step keeps them and only tops
+    up when they are few; reset() forgets frame and points."""
+    frames, imus, kw = tc.build("exp")
+    kw = dict(kw, min_features=3)
+    trk = make_gpu_tracker(ofb200, ctx, kw, 1)
+    try:
+        seed = np.array([[50.0, 60.0], [200.0, 100.0], [120.0, 180.0], [260.0, 40.0], [30.0, 200.0]], np.float32)
+        trk.set_points(seed)
+        im = imu_records(ofb200, [imus[0][0]])
+        res, pts = trk.step(frames[0][0], im, want_points=True)
+        assert res["n_prev"][0] == 5 and res["n_added"][0] == 0 and not (res["flags"][0] & 1)
+        assert np.array_equal(pts[0].reshape(-1, 2), seed)
+        res, pts = trk.step(frames[0][1], imu_records(ofb200, [imus[0][1]]), want_points=True)
+        exp, st, _ = io.pyrlk(frames[0][0], frames[0][1], seed, win=(15, 15), max_level=3, criteria=(3, 20, 0.03))
+        assert res["n_tracked"][0] == int(st.sum())
+        assert close_positions(pts[0].reshape(-1, 2)[:int(st.sum())], exp.reshape(-1, 2)[st.reshape(-1) == 1], LK_TOL)
+        trk.reset()
+        res, pts = trk.step(frames[0][2], im, want_points=True)
+        assert res["n_prev"][0] == 0 and res["n_tracked"][0] == 0 and res["n_added"][0] == res["n_points"][0] > 0
+    finally:
+        trk.close()
+
+
+def test_invalid_configurations_raise(ofb200, ctx):
+    with pytest.raises(ValueError):
+        ofb200.StreamTracker(320, 240, max_features=10, min_features=10, ctx=ctx)
+    with pytest.raises(ValueError):
+        ofb200.StreamTracker(320, 240, n_streams=0, ctx=ctx)
+    trk = ofb200.StreamTracker(320, 240, ctx=ctx)
+    try:
+        with pytest.raises(ValueError):
+            trk.step(np.zeros((100, 100), np.uint8), np.zeros(1, ofb200._lib.IMU_DTYPE))
+        with pytest.raises(ValueError):
+            trk.set_points(np.zeros((trk.capacity + 1, 2), np.float32))
+    finally:
+        trk.close()
+
+
+def test_fleet_size_streams_match_single_stream(ofb200, ctx):
+    """Fleet shape (scaled to 24 streams of 1280x720, 500 features): streams 0, 11 and 23 of the
+    fleet tracker equal single-stream trackers run on the same frames."""
+    import synth
+    w, h, S, T = 1280, 720, 24, 3
+    base = [synth.texture(h + 16, w + 16, 40 + i) for i in range(3)]
+    frames = [[np.ascontiguousarray(base[s % 3][2 * k + (s % 5):2 * k + (s % 5) + h, 3 * k + (s % 7):3 * k + (s % 7) + w]) for k in range(T)]
+              for s in range(S)]
+    kw = dict(max_features=500, min_features=480, topup="node", mask_radius=12, variant="node", scaling=1.0 / (0.8 * w),
+              lk_params=dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03)))
+    imu = np.zeros(S, ofb200._lib.IMU_DTYPE)
+    imu["d"], imu["n"] = 1.5, [0.0, 0.0, 1.0]
+
+    def run(sel):
+        trk = ofb200.StreamTracker(w, h, n_streams=len(sel), ctx=ctx, **kw)
+        try:
+            return [trk.step(np.stack([frames[s][k] for s in sel]), imu[sel], want_points=True) for k in range(T)]
+        finally:
+            trk.close()
+    fleet = run(list(range(S)))
+    assert fleet[0][0]["n_points"].min() == 500
+    assert fleet[T - 1][0]["n_tracked"].min() > 400 and (fleet[T - 1][0]["flags"] & 1).all()
+    for s in (0, 11, 23):
+        single = run([s])
+        for k in range(T):
+            assert same_record(fleet[k][0][s], single[k][0][0]), "stream %d step %d" % (s, k)
+            assert np.array_equal(fleet[k][1][s], single[k][1][0])
+    # pure shift by (3, 2) px per frame at height 1.5 m: v = -(3, 2) / f * d
+    v = fleet[T - 1][0]["v"]
+    assert np.abs(v[:, 0] + 3 * 1.5 / (0.8 * w)).max() < 2e-4 and np.abs(v[:, 1] + 2 * 1.5 / (0.8 * w)).max() < 2e-4
