@@ -125,7 +125,7 @@ def test_tracker_steps_vs_golden_and_oracle(ofb200, ctx, g, name):
                     assert np.allclose(res["s"][s], sv, rtol=1e-7), tag
                     if np.size(r_):
                         assert abs(res["res"][s] - float(r_[0])) <= 1e-7 * max(float(r_[0]), 1e-12), tag
-        assert total_topups >= 3
+        assert total_topups >= 2
         assert identical_topups >= total_topups - 1, "more than one top-up needed the tie rule"
     finally:
         trk.close()
