@@ -13,7 +13,7 @@ no CPU fallback: without the built library or without a B200 every call raises.
 """
 from . import _lib
 from ._lib import Context, OfbError, default_context
-from . import of_library, velocity, vision, simulation, tracker
+from . import of_library, velocity, vision, simulation, tracker, replay
 from .of_library import pix_trans, r_tilde, static_immobile, initialize_ft
 from .velocity import (solve_lgs, solve_full, solve_lgs_batched, generate_test_data, feasibility,
                        quaternion_to_rotation, plane_normal, body_to_world)

@@ -251,3 +251,63 @@ def test_fleet_size_streams_match_single_stream(ofb200, ctx):
     # pure shift by (3, 2) px per frame at height 1.5 m: v = -(3, 2) / f * d
     v = fleet[T - 1][0]["v"]
     assert np.abs(v[:, 0] + 3 * 1.5 / (0.8 * w)).max() < 2e-4 and np.abs(v[:, 1] + 2 * 1.5 / (0.8 * w)).max() < 2e-4
+
+
+def test_replay_flight_end_to_end(ofb200, ctx):
+    """evaluate_exp.py:77-120 through ofb200.replay: nearest IMU / sonar sample per frame, then the tracker. The
+    result equals stepping the tracker by hand with the associated samples."""
+    from ofb200 import replay
+    frames, imus, kw = tc.build("exp")
+    T = len(frames[0])
+    M = replay.RosMessage
+    cam_t = 0.05 * np.arange(T)
+    imu_msgs, rng_msgs = [], []
+    for k in range(3 * T):                                             # IMU at 3x the camera rate, offset by 4 ms
+        q = np.array([0.01 * np.sin(k), 0.02 * np.cos(k), 0.1, 1.0]); q /= np.linalg.norm(q)
+        stamp = M("Time", [100 + int((0.004 + k * 0.05 / 3) // 1), int(((0.004 + k * 0.05 / 3) % 1) * 1e9)])
+        imu_msgs.append(M("Imu", [M("Header", [k, stamp, "fcu"]), M("Quaternion", list(q)), [0.0] * 9,
+                                  M("Vector3", [0.01 * k, -0.02, 0.03]), [0.0] * 9, M("Vector3", [0, 0, 9.81]), [0.0] * 9]))
+    for k in range(2 * T):
+        stamp = M("Time", [100, int((0.01 + k * 0.025) * 1e9)])
+        rng_msgs.append(M("Range", [M("Header", [k, stamp, "sonar"]), 0, 0.0, 0.2, 7.0, 1.0 + 0.01 * k]))
+    it, rt = replay.stamps(imu_msgs, 100), replay.stamps(rng_msgs, 100)
+    trk = make_gpu_tracker(ofb200, ctx, kw, 1)
+    try:
+        got = [(k, r.copy(), s.copy()) for k, r, s in replay.replay_flight(frames[0], cam_t, imu_msgs, it, rng_msgs, rt, trk,
+                                                                          translation=(0.02, 0.0, 0.205))]
+    finally:
+        trk.close()
+    ii, hi = replay.nearest(it, cam_t), replay.nearest(rt, cam_t)
+    assert ii.tolist() == [int(np.argmin(np.abs(it - t))) for t in cam_t]
+    samples = replay.imu_samples(imu_msgs, rng_msgs, ii, hi, (0.02, 0.0, 0.205))
+    trk = make_gpu_tracker(ofb200, ctx, kw, 1)
+    try:
+        for k in range(T):
+            r = trk.step(frames[0][k], samples[k:k + 1])
+            assert same_record(r[0], got[k][1]), "frame %d" % k
+            assert got[k][2]["d"] == rng_msgs[hi[k]].range
+    finally:
+        trk.close()
+    assert sum(int(g_[1]["flags"]) & 1 for g_ in got) == T - 1
+
+
+def test_initialize_ft_as_intended(ofb200, ctx):
+    """of_library.py:231-263 (8f-3): first frame -> goodFeaturesToTrack -> LK steps with the dynamic-immobile filter ->
+    eval_ft ranking; ValueError for non-positive iterations / end_count (of_library.py:240-243)."""
+    import ofb200.of_library as of
+    frames, _, _ = tc.build("exp")
+    fp = dict(maxCorners=40, qualityLevel=0.05, minDistance=10, blockSize=7)
+    lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
+    # the window drifts by (7.5, -3.25) px per frame: with f = 256 px and height 2 m the camera moves at
+    # v = flow * Z / f; a generous velocity error keeps every static point inside the immobile band
+    f, Z = 256.0, 2.0
+    vel = np.array([-7.5 * Z / f, 3.25 * Z / f, 0.0])
+    with pytest.raises(ValueError):
+        of.initialize_ft(list(frames[0]), fp, lk, 0, 10, vel, 0.5 * np.ones(3), f, -1.0, (tc.W, tc.H), [1, 1, 1, 1])
+    with pytest.raises(ValueError):
+        of.initialize_ft(list(frames[0]), fp, lk, 2, 0, vel, 0.5 * np.ones(3), f, -1.0, (tc.W, tc.H), [1, 1, 1, 1])
+    h, he, pos, perr = of.initialize_ft(list(frames[0][:4]), fp, lk, 3, 10, vel, 0.5 * np.ones(3), f, -1.0, (tc.W, tc.H),
+                                        [0, 1, 0, 0])
+    assert len(h) == len(he) == len(pos) == len(perr) and 10 <= len(h) <= 40
+    assert np.all(np.diff(he) >= 0), "eval_ft with weight on the height error sorts by it"
+    assert np.abs(np.median(np.abs(h)) - Z) < 0.5 * Z
