@@ -323,6 +323,21 @@ def extra_workload(args):
         e2e_lat = []
         for _ in range(max(args.steps, 50)):
             t0 = time.perf_counter(); ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx); e2e_lat.append((time.perf_counter() - t0) * 1e3)
+        # the same camera through the device-resident feature lifecycle (ofb200.StreamTracker.step: one pageable host
+        # frame in, one result record out per call) -- what velocity_measurment_node's image callback would run
+        trk = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2,
+                                   feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+                                   lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
+                                   variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
+                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=ctx)
+        for k in range(6):
+            tres = trk.step(hb if k & 1 else ha, imu[:1])
+        trk_lat = []
+        for k in range(max(args.steps, 50)):
+            t0 = time.perf_counter(); tres = trk.step(hb if k & 1 else ha, imu[:1]); trk_lat.append((time.perf_counter() - t0) * 1e3)
+        trk.close()
+        lifecycle = {"host_call_ms_p50": float(np.percentile(trk_lat, 50)), "host_call_ms_p95": float(np.percentile(trk_lat, 95)),
+                     "n_tracked": int(tres["n_tracked"][0]), "solved": int(tres["flags"][0] & 1)}
         cpu_ms = None
         if not args.no_cpu:
             try:
@@ -332,7 +347,7 @@ def extra_workload(args):
                 cpu_ms = {"unavailable": repr(e)}
         name = "3840x2160" if args.workload == "c4" else "640x480"
         line = {"metric": name + " frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
-                "e2e_host_call_ms_p50": float(np.percentile(e2e_lat, 50)), "cpu_reference": cpu_ms,
+                "e2e_host_call_ms_p50": float(np.percentile(e2e_lat, 50)), "lifecycle_step": lifecycle, "cpu_reference": cpu_ms,
                 "stage_ms_serial": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s / max(calls, 1), 4) for s in sms])),
                 "unit": "ms", "p95": float(np.percentile(lat, 95)), "n_gpus": 1, "steps": len(lat), "higher_is_better": False,
                 "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call" if args.workload == "c4"

@@ -198,28 +198,36 @@ __global__ void mask_fill_kernel(uint8_t* __restrict__ mask, size_t mstride, con
 {
     const int s = blockIdx.y;
     if (need && !need[s]) return;
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i < mstride) *(uint4*)(mask + (size_t)s * mstride + i) = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    uint4* m = (uint4*)(mask + (size_t)s * mstride);
+    const size_t n16 = mstride / 16;                                  // mstride is a multiple of 256
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        m[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
 }
 
 // cv2.circle(mask, (int(x), int(y)), radius, 0, FILLED): clipped union of the midpoint-circle spans; hw[|dy|] is the
-// half width of row cy+dy (computed once on the host from OpenCV's loop). One CTA per point, threads over rows.
-__global__ void mask_circle_kernel(uint8_t* __restrict__ mask, int w, int h, int mpitch, size_t mstride,
-                                   const float* __restrict__ pts, size_t pts_stride, const int* __restrict__ count,
-                                   const int* __restrict__ need, const int* __restrict__ hw, int radius)
+// half width of row cy+dy (computed once on the host from OpenCV's loop). MASK_CTAS CTAs per stream walk the points;
+// per point the warps take the rows and the lanes the bytes of a row (coalesced stores). Streams that need no top-up
+// cost one exiting CTA row.
+#define MASK_CTAS 8
+__global__ void __launch_bounds__(256)
+mask_circle_kernel(uint8_t* __restrict__ mask, int w, int h, int mpitch, size_t mstride, const float* __restrict__ pts,
+                   size_t pts_stride, const int* __restrict__ count, const int* __restrict__ need,
+                   const int* __restrict__ hw, int radius)
 {
-    const int s = blockIdx.y, i = blockIdx.x;
+    const int s = blockIdx.y;
     if (need && !need[s]) return;
-    if (i >= count[s]) return;
-    const float fx = pts[2 * ((size_t)s * pts_stride + i)], fy = pts[2 * ((size_t)s * pts_stride + i) + 1];
-    const int cx = (int)fx, cy = (int)fy;                             // Python-2 cv2 truncates float coordinates
+    const int n = count[s], lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint8_t* m = mask + (size_t)s * mstride;
-    for (int r = threadIdx.x; r <= 2 * radius; r += blockDim.x) {
-        const int dy = r - radius, y = cy + dy;
-        if (y < 0 || y >= h) continue;
-        const int half = hw[dy < 0 ? -dy : dy];
-        const int x0 = max(cx - half, 0), x1 = min(cx + half, w - 1);
-        for (int x = x0; x <= x1; ++x) m[(size_t)y * mpitch + x] = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const float fx = pts[2 * ((size_t)s * pts_stride + i)], fy = pts[2 * ((size_t)s * pts_stride + i) + 1];
+        const int cx = (int)fx, cy = (int)fy;                         // Python-2 cv2 truncates float coordinates
+        for (int r = warp; r <= 2 * radius; r += nwarps) {
+            const int dy = r - radius, y = cy + dy;
+            if (y < 0 || y >= h) continue;
+            const int half = hw[dy < 0 ? -dy : dy];
+            const int x0 = max(cx - half, 0), x1 = min(cx + half, w - 1);
+            for (int x = x0 + lane; x <= x1; x += 32) m[(size_t)y * mpitch + x] = 0;
+        }
     }
 }
 
@@ -268,12 +276,13 @@ int render_mask_device(ofb_ctx* ctx, uint8_t* mask, int w, int h, int mpitch, si
                        const float* pts, size_t pts_stride, int max_pts, const int* count, const int* need, const int* hw,
                        int radius)
 {
-    dim3 fg((unsigned int)((mstride / 16 + 255) / 256), n_streams);
+    const unsigned int fill_ctas = (unsigned int)((mstride / 16 + 255) / 256);
+    dim3 fg(fill_ctas < 16 ? fill_ctas : 16, n_streams);
     mask_fill_kernel<<<fg, 256, 0, ctx->stream>>>(mask, mstride, need);
     OFB_LAUNCH_CHECK(ctx);
     if (max_pts > 0 && radius >= 0) {
-        dim3 cg(max_pts, n_streams);
-        mask_circle_kernel<<<cg, 64, 0, ctx->stream>>>(mask, w, h, mpitch, mstride, pts, pts_stride, count, need, hw, radius);
+        dim3 cg(max_pts < MASK_CTAS ? max_pts : MASK_CTAS, n_streams);
+        mask_circle_kernel<<<cg, 256, 0, ctx->stream>>>(mask, w, h, mpitch, mstride, pts, pts_stride, count, need, hw, radius);
         OFB_LAUNCH_CHECK(ctx);
     }
     return OFB_OK;
