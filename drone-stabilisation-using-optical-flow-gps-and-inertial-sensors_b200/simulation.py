@@ -240,8 +240,34 @@ def feas_simulation(linear_velocity, angular_velocity, height_above_gr, normal_v
     return m[0], m[1], m[2], m[3], m[4], m[5]
 
 
-def overlap(data1, data2, ctx=None):
-    """simulation.py:124-136: common 100-bin histogram over the pooled range, sum of bin-wise minima."""
+def merge_range(lo, hi, group=None, device=None):
+    """All-reduce(min) / (max) of a shard's value range (the common histogram edges of `overlap` come from
+    the pooled sample). Empty shards pass lo=+inf, hi=-inf."""
+    import torch
+    import torch.distributed as dist
+    a = torch.tensor([lo], dtype=torch.float64, device=device)
+    b = torch.tensor([hi], dtype=torch.float64, device=device)
+    dist.all_reduce(a, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
+    return float(a.item()), float(b.item())
+
+
+def merge_counts(counts, group=None, device=None):
+    """All-reduce(sum) of histogram bin counts (int64 on the wire)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(counts).astype(np.int64))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def overlap(data1, data2, ctx=None, distributed=False, group=None):
+    """simulation.py:124-136: common 100-bin histogram over the pooled range, sum of bin-wise minima.
+    distributed=True: data1/data2 are this rank's SHARDS of the two samples (e.g. the v_obs dumps of its trial range);
+    the range is merged with all-reduce(min/max), the bin counts with all-reduce(sum), and every rank returns the
+    overlap of the full samples."""
     ctx = ctx or _lib.default_context()
     d1 = np.ascontiguousarray(data1, dtype=np.float64).reshape(-1)
     d2 = np.ascontiguousarray(data2, dtype=np.float64).reshape(-1)
@@ -251,16 +277,47 @@ def overlap(data1, data2, ctx=None):
             lo, hi = C.c_double(), C.c_double()
             _lib.check(ctx.lib.ofb_minmax(ctx.h, _lib.ptr(d), len(d), C.byref(lo), C.byref(hi)))
             los.append(lo.value); his.append(hi.value)
-    if not los:
-        return 0
-    lo, hi = min(los), max(his)
+    dev = None
+    if distributed:
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", ctx.device) if dist.get_backend(group) == "nccl" else None
+        lo, hi = merge_range(min(los) if los else np.inf, max(his) if his else -np.inf, group, dev)
+        if not np.isfinite(lo):
+            return 0
+    else:
+        if not los:
+            return 0
+        lo, hi = min(los), max(his)
     hists = []
     for d in (d1, d2):
         cnt = np.zeros(100, np.uint64)
         if len(d):
             _lib.check(ctx.lib.ofb_histogram(ctx.h, _lib.ptr(d), len(d), lo, hi, 100, _lib.ptr(cnt)))
         hists.append(cnt)
+    if distributed:
+        both = merge_counts(np.concatenate(hists), group, dev)
+        hists = [both[:100], both[100:]]
     return int(np.sum(np.minimum(hists[0], hists[1])))
+
+
+def stream_shard(n_streams, rank, world):
+    """Camera streams of `rank` (gpu = stream_id mod n_gpu, no data-path collective)."""
+    return list(range(int(rank), int(n_streams), int(world)))
+
+
+def gather_stream_velocities(v_local, stream_ids, n_streams, group=None, device=None):
+    """Final gather of the per-stream velocities of a sharded fleet (3 doubles per stream): every rank contributes
+    its streams' rows to an (n_streams, 3) table, merged with one all-reduce(sum) (rows are disjoint)."""
+    import torch
+    import torch.distributed as dist
+    table = np.zeros((int(n_streams), 3))
+    table[np.asarray(stream_ids, dtype=np.int64)] = np.asarray(v_local, dtype=np.float64).reshape(-1, 3)
+    t = torch.from_numpy(table)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
 
 
 # ---- sweep drivers (simulation.py:183-578; SURVEY App. C) ------------------------------------------

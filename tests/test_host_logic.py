@@ -123,3 +123,48 @@ def test_merge_sums_world_size_2_gloo():
         assert m[1, 1] == pytest.approx(ids.sum() * 2) and m[2, 3] == pytest.approx(-ids.sum())
         assert m[0, 4] == pytest.approx((ids ** 2).sum()) and m[0, 7] == pytest.approx(ids.sum())
     assert outs[0][1] == outs[1][1]
+
+
+def _hist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ofb200 import simulation as sim
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.default_rng(9)
+    d1, d2 = rng.normal(0, 1, 5000), rng.normal(0.7, 1.3, 4000)
+    b1, c1 = sim.shard_range(len(d1), rank, world)
+    b2, c2 = sim.shard_range(len(d2), rank, world)
+    s1, s2 = d1[b1:b1 + c1], d2[b2:b2 + c2]
+    lo, hi = sim.merge_range(min(s1.min(), s2.min()), max(s1.max(), s2.max()))
+    # numpy's histogram binning over the merged range stands in for ofb_histogram (same contract, GPU-tested)
+    h = np.concatenate([np.histogram(s1, bins=100, range=(lo, hi))[0], np.histogram(s2, bins=100, range=(lo, hi))[0]])
+    both = sim.merge_counts(h)
+    ids = sim.stream_shard(7, rank, world)
+    v = sim.gather_stream_velocities(np.array([[i, 2.0 * i, -i] for i in ids], dtype=float), ids, 7)
+    q.put((rank, lo, hi, int(np.minimum(both[:100], both[100:]).sum()), v.tolist()))
+    dist.destroy_process_group()
+
+
+def test_overlap_merge_and_stream_gather_world_size_2_gloo():
+    """range all-reduce(min/max) then bin-count all-reduce(sum) reproduce the single-process overlap
+    (simulation.py:124-136); stream-sharded velocities gather into one table."""
+    import torch.multiprocessing as mp
+    from oracle import velocity_oracle as vo
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(9)
+    d1, d2 = rng.normal(0, 1, 5000), rng.normal(0.7, 1.3, 4000)
+    expect = vo.overlap(d1, d2)
+    for rank, lo, hi, ov, v in outs:
+        assert lo == min(d1.min(), d2.min()) and hi == max(d1.max(), d2.max())
+        assert ov == expect
+        assert np.array_equal(np.array(v), np.array([[i, 2.0 * i, -i] for i in range(7)], dtype=float))
