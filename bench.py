@@ -367,7 +367,7 @@ def extra_workload(args):
                                    feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
                                    lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
                                    variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
-                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=ctx)
+                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), borrow_frames=True, ctx=ctx)
         d_tres = torch.zeros(B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
 
         def tstep(k):
@@ -391,7 +391,7 @@ def extra_workload(args):
         lifecycle = {"value": 256 * 2 * args.steps / (tms * 1e-3), "unit": "pairs/s", "ms_per_step": tms / (2 * args.steps),
                      "gpu_launches_per_step": tl / (2 * args.steps),
                      "what": "ofb_tracker_step: new frame -> pyramid -> LK from the kept frame -> status filter -> solve -> "
-                             "(masked top-up when <= %d points survive); resident frames" % (feat // 2),
+                             "(masked top-up when <= %d points survive); resident frames used in place (borrow_frames)" % (feat // 2),
                      "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
                                "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
         line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "lifecycle": lifecycle, "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",

@@ -41,7 +41,8 @@ class PairResult(C.Structure):
 class TrackerCfg(C.Structure):
     _fields_ = [("pair", PairCfg), ("n_streams", C.c_int), ("min_features", C.c_int), ("topup_mode", C.c_int),
                 ("mask_radius", C.c_int), ("bgr_input", C.c_int), ("max_speed", C.c_double),
-                ("dummy_value", C.c_double), ("gate_mode", C.c_int), ("gate_T", C.c_double), ("min_solve", C.c_int)]
+                ("dummy_value", C.c_double), ("gate_mode", C.c_int), ("gate_T", C.c_double), ("min_solve", C.c_int),
+                ("borrow_frames", C.c_int)]
 
 
 class TrackResult(C.Structure):

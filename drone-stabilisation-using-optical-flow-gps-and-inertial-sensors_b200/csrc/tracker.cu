@@ -404,8 +404,11 @@ extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch
     const void *dimu, *dvp = nullptr;
     OFB_TRY(ofb_stage_in(ctx, SC_IN3, imu, sizeof(ofb_imu_sample) * S, &dimu));
     if (v_prior) OFB_TRY(ofb_stage_in(ctx, SC_IN4, v_prior, sizeof(double) * 3 * S, &dvp));
-    // 1. ingest: the tracker keeps its own copy of the frame (it is "old_image" of the next step)
-    uint8_t* f = t->frames[t->cur].as<uint8_t>();
+    // 1. ingest: the tracker keeps its own copy of the frame (it is "old_image" of the next step) unless the caller
+    //    lends device-resident frames (borrow_frames)
+    const uint8_t* f = t->frames[t->cur].as<uint8_t>();
+    uint8_t* fown = t->frames[t->cur].as<uint8_t>();
+    int fpitch = t->pitch_d; size_t fstride = t->stride_d;
     if (cfg.bgr_input) {
         const uint8_t* src = frames; int spitch = pitch; size_t sstride = image_stride;
         if (!ofb_is_device_ptr(frames)) {
@@ -418,16 +421,18 @@ extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch
         }
         const int vec = ((uintptr_t)src % 4 == 0 && spitch % 4 == 0 && sstride % 4 == 0) ? 1 : 0;
         dim3 grid(ofb_div_up(ofb_div_up(w, 4), 128), h, S);
-        ingest_bgr_kernel<<<grid, 128, 0, ctx->stream>>>(src, w, h, spitch, sstride, f, t->pitch_d, t->stride_d, vec);
+        ingest_bgr_kernel<<<grid, 128, 0, ctx->stream>>>(src, w, h, spitch, sstride, fown, t->pitch_d, t->stride_d, vec);
         OFB_LAUNCH_CHECK(ctx);
+    } else if (cfg.borrow_frames && ofb_is_device_ptr(frames)) {
+        f = frames; fpitch = pitch; fstride = image_stride;
     } else if (pitch == t->pitch_d && (S == 1 || image_stride == t->stride_d)) {
-        OFB_CUDA(cudaMemcpyAsync(f, frames, t->stride_d * (size_t)(S - 1) + (size_t)pitch * (h - 1) + w, cudaMemcpyDefault, ctx->stream));
+        OFB_CUDA(cudaMemcpyAsync(fown, frames, t->stride_d * (size_t)(S - 1) + (size_t)pitch * (h - 1) + w, cudaMemcpyDefault, ctx->stream));
     } else {
         for (int s = 0; s < S; ++s)
-            OFB_CUDA(cudaMemcpy2DAsync(f + (size_t)s * t->stride_d, t->pitch_d, frames + (size_t)s * image_stride, pitch, w, h,
+            OFB_CUDA(cudaMemcpy2DAsync(fown + (size_t)s * t->stride_d, t->pitch_d, frames + (size_t)s * image_stride, pitch, w, h,
                                        cudaMemcpyDefault, ctx->stream));
     }
-    OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, t->pitch_d, t->stride_d, S, S, pc.max_level, true));
+    OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, fpitch, fstride, S, S, pc.max_level, true));
     int* count = t->counts.as<int>();
     int* need = count + S;
     int* keptn = count + 2 * S;
@@ -469,7 +474,7 @@ extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch
     FeatImageState* st = nullptr;
     const unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
     ctx->feat_active = need;
-    int fr = ofb_features_device(ctx, f, w, h, t->pitch_d, t->stride_d, S, mask, t->pitch_d, t->stride_d, K, pc.quality,
+    int fr = ofb_features_device(ctx, f, w, h, fpitch, (S == 1 ? 0 : fstride), S, mask, t->pitch_d, t->stride_d, K, pc.quality,
                                  pc.min_distance, pc.block_size, cand_cap, t->det.as<float>(), (size_t)2 * K, K, &st);
     ctx->feat_active = nullptr;
     OFB_TRY(fr);

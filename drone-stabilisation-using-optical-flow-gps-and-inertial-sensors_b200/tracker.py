@@ -26,12 +26,14 @@ class StreamTracker:
            "node" -> node:157-172 (circles of mask_radius around surviving points, maxCorners=max_features-count),
            "module" -> of_module.py:83-86 (the set is replaced).
     gate: None, ("ge", T) (of_module.py:129) or ("le", T) (node:240-245) on of.r_tilde(x, u, n, v_prior, d).
-    max_speed > 0 enables of.static_immobile(new, old, max_speed, d, dummy_value)."""
+    max_speed > 0 enables of.static_immobile(new, old, max_speed, d, dummy_value).
+    borrow_frames: device-resident grey frames (CUDA tensors) are tracked in place instead of being copied into the
+    tracker; pass a NEW tensor every step (the tracker keeps the previous one alive; do not overwrite it)."""
 
     def __init__(self, width, height, max_features=100, min_features=20, n_streams=1, feature_params=None,
                  lk_params=None, topup="exp", mask_radius=30, bgr=False, variant="exp", principal=None,
                  scaling=1.0, flow_scaling=None, max_speed=0.0, dummy_value=float("nan"), gate=None, min_solve=3,
-                 min_eig_thr=1e-4, ctx=None):
+                 min_eig_thr=1e-4, borrow_frames=False, ctx=None):
         fp = dict(qualityLevel=0.01, minDistance=10, blockSize=7)
         fp.update(feature_params or {})
         lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
@@ -55,6 +57,8 @@ class StreamTracker:
             cfg.gate_mode = {"ge": _lib.GATE_R_GE, "le": _lib.GATE_R_LE}[gate[0]]
             cfg.gate_T = float(gate[1])
         cfg.min_solve = int(min_solve)
+        cfg.borrow_frames = 1 if borrow_frames else 0
+        self._held = []          # borrow_frames: the last two device frames stay referenced until they are no longer read
         self.cfg = cfg
         self.n_streams, self.width, self.height, self.bgr = int(n_streams), int(width), int(height), bool(bgr)
         h = C.c_void_p()
@@ -107,8 +111,11 @@ class StreamTracker:
             raise ValueError("frames must have shape %r, got %r" % ((S,) + tail, tuple(frames.shape)))
         if isinstance(frames, np.ndarray):
             frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        elif not frames.is_contiguous():
-            frames = frames.contiguous()
+        else:
+            if not frames.is_contiguous():
+                frames = frames.contiguous()
+            if self.cfg.borrow_frames:
+                self._held = (self._held + [frames])[-2:]
         bpp = 3 if self.bgr else 1
         imu = np.ascontiguousarray(imu, dtype=_lib.IMU_DTYPE).reshape(-1)
         if len(imu) != S:

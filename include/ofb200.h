@@ -226,6 +226,9 @@ typedef struct {
     int    gate_mode;        /* OFB_GATE_* on of.r_tilde(x, u, n, v_prior, d) */
     double gate_T;
     int    min_solve;        /* solve only when at least this many points are kept (3 at node:247) */
+    int    borrow_frames;    /* 1: device-resident grey frames are used in place instead of being copied into the
+                                tracker; the caller keeps frame k unchanged until step k+1 has completed (a ring of
+                                two buffers per stream is enough). Ignored for host or BGR frames. */
 } ofb_tracker_cfg;
 
 typedef struct {

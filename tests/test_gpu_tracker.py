@@ -131,10 +131,10 @@ def test_tracker_steps_vs_golden_and_oracle(ofb200, ctx, g, name):
         trk.close()
 
 
-def run_free(ofb200, ctx, kw, frames, imus, device_frames=False):
+def run_free(ofb200, ctx, kw, frames, imus, device_frames=False, borrow=False):
     import torch
     S, T = len(frames), len(frames[0])
-    trk = make_gpu_tracker(ofb200, ctx, kw, S)
+    trk = make_gpu_tracker(ofb200, ctx, dict(kw, borrow_frames=borrow), S)
     out = []
     try:
         for k in range(T):
@@ -174,6 +174,10 @@ def test_streams_are_independent_and_device_frames_match(ofb200, ctx, name):
         imus = [imus[0], imus[0][::-1], imus[0]]
     both = run_free(ofb200, ctx, kw, frames, imus)
     dev = run_free(ofb200, ctx, kw, frames, imus, device_frames=True)
+    lent = run_free(ofb200, ctx, kw, frames, imus, device_frames=True, borrow=True)      # frames used in place
+    for k in range(len(frames[0])):
+        for s in range(len(frames)):
+            assert same_record(lent[k][0][s], dev[k][0][s]) and np.array_equal(lent[k][1][s], dev[k][1][s])
     for s in range(len(frames)):
         single = run_free(ofb200, ctx, kw, [frames[s]], [imus[s]])
         for k in range(len(frames[0])):
