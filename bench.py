@@ -394,6 +394,53 @@ def extra_workload(args):
                              "(masked top-up when <= %d points survive); resident frames used in place (borrow_frames)" % (feat // 2),
                      "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
                                "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
+        # end to end: the fleet's frames arrive in (pinned) HOST memory every step. Four sub-fleets on four contexts
+        # (own streams): the H2D copy of one sub-fleet overlaps the kernels of the others; every step's result records
+        # are read back to the host. Bytes per step: B frames in, B result records out.
+        NSUB = 4 if B >= 8 else 1
+        bounds = [B * i // NSUB for i in range(NSUB + 1)]
+        subs = []
+        for i in range(NSUB):
+            n_i = bounds[i + 1] - bounds[i]
+            c_i = ofb200.Context(local)
+            t_i = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2, n_streams=n_i,
+                                       feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+                                       lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
+                                       variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
+                                       flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=c_i)
+            ha_i = torch.from_numpy(np.stack([pairs[j % distinct][0] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
+            hb_i = torch.from_numpy(np.stack([pairs[j % distinct][1] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
+            dimu_i = torch.from_numpy(imu[bounds[i]:bounds[i + 1]].view(np.uint8).reshape(-1).copy()).cuda()
+            dres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            hres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            subs.append((c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i))
+        torch.cuda.synchronize()
+
+        def estep(k):
+            for c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i in subs:
+                ofb200._lib.check(c_i.lib.ofb_tracker_step(t_i.h, P(hb_i if k & 1 else ha_i), w, w * h, P(dimu_i), None, P(dres_i),
+                                                           None, None, None, None))
+                ofb200._lib.check(c_i.lib.ofb_memcpy_async(c_i.h, P(hres_i), P(dres_i), hres_i.numel()))
+            for sub in subs:
+                sub[0].sync()
+        for k in range(2 * max(args.warmup, 1)):
+            estep(k)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(2 * args.steps):
+            estep(k)
+        torch.cuda.synchronize()
+        ems = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ems], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ems = float(t.item())
+        eres = np.concatenate([sub[6].numpy().view(ofb200._lib.TRACK_RESULT_DTYPE) for sub in subs])
+        for sub in subs:
+            sub[1].close()
+        lifecycle["e2e"] = {"value": 256 * 2 * args.steps / (ems * 1e-3), "unit": "pairs/s", "ms_per_step": ems / (2 * args.steps),
+                            "h2d_bytes_per_step": B * w * h, "d2h_bytes_per_step": B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize,
+                            "sub_fleets": NSUB, "check": {"min_tracked": int(eres["n_tracked"].min()), "solved": int((eres["flags"] & 1).sum())}}
         line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "lifecycle": lifecycle, "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "config": {"workload": "C5: 256 streams x 1280x720, 500 features, maxLevel 3, stream-sharded", "streams_per_gpu": B},
