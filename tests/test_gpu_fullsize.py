@@ -110,3 +110,43 @@ def test_c3_full_size_monte_carlo_properties(ctx, points200):
     assert np.all(np.abs(s2[ok] / std[ok] - 1) <= 5 / np.sqrt(2e5))
     # no noise at step 0 (flow_sig = position_sig = 0): the only scatter left is gyro/height/lever-arm noise
     assert std[0].max() < 0.03 and std[99].max() > std[0].max()
+
+
+def test_c4_lifecycle_at_4k(ctx, frame4k):
+    """Feature lifecycle (ofb_tracker_step) at the C4 shape: 3840x2160, 5000 features, maxLevel 5. Step 1 detects
+    (cluster-mode selection), step 2 tracks and -- with min_features just below the maximum -- runs a masked top-up.
+    Tracks equal the pair path bit for bit; the appended corners equal OpenCV's selection rule on the GPU's own
+    lambda_min map under the cv2.circle exclusion mask of the surviving points."""
+    import ofb200
+    from oracle import tracker_oracle
+    a, b, mo = frame4k
+    K, R = 5000, 12
+    trk = ofb200.StreamTracker(3840, 2160, max_features=K, min_features=K - 1, topup="node", mask_radius=R, variant="node",
+                               principal=(mo["cx"], mo["cy"]), scaling=1.0 / mo["f"], flow_scaling=1.0 / (mo["f"] * mo["dt"]),
+                               lk_params=dict(winSize=(15, 15), maxLevel=5, criteria=(3, 20, 0.03)), ctx=ctx)
+    imu = np.zeros(1, ofb200._lib.IMU_DTYPE)
+    imu["d"], imu["n"], imu["w"] = mo["d"], mo["n"], mo["w"]
+    try:
+        r0, p0 = trk.step(a, imu, want_points=True)
+        r1, p1, kp, kn = trk.step(b, imu, want_points=True, want_kept=True)
+    finally:
+        trk.close()
+    pts = ofb200.goodFeaturesToTrack(a, K, 0.01, 10, blockSize=7, ctx=ctx)
+    assert int(r0["n_added"][0]) == K and np.array_equal(p0[0], pts)
+    n, s, e = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, winSize=(15, 15), maxLevel=5, criteria=(3, 20, 0.03), ctx=ctx)
+    ok = s.ravel() == 1
+    assert int(r1["n_tracked"][0]) == int(ok.sum()) == int(r1["n_kept"][0]) and ok.sum() > 4800
+    assert np.array_equal(kp[0], pts.reshape(-1, 2)[ok]) and np.array_equal(kn[0], n.reshape(-1, 2)[ok])
+    cfg = ofb200.make_pair_cfg(3840, 2160, K, 0.01, 10, 7, (15, 15), 5, (3, 20, 0.03), variant="node",
+                               principal=(mo["cx"], mo["cy"]), pos_scale=1.0 / mo["f"], flow_scale=1.0 / (mo["f"] * mo["dt"]))
+    res = ofb200.frame_pairs(a[None], b[None], imu, cfg, ctx=ctx)
+    assert np.abs(r1["v"][0] - res["v"][0]).max() <= 1e-12 * max(1.0, np.abs(res["v"][0]).max())
+    # masked top-up on frame 2
+    na = int(r1["n_added"][0])
+    assert na == K - int(ok.sum()) or na < K - int(ok.sum())          # fewer when the unmasked area runs out of corners
+    mask = tracker_oracle.exclusion_mask(kn[0], R, 3840, 2160)
+    assert np.array_equal(mask, ofb200.exclusion_mask(kn[0], R, 3840, 2160, ctx=ctx))
+    eig = ofb200.cornerMinEigenVal(b, 7, ctx=ctx)
+    expect = io.select_features(eig, K - int(ok.sum()), 0.01, 10, mask)
+    expect = np.zeros((0, 2), np.float32) if expect is None else expect.reshape(-1, 2)
+    assert na == len(expect) and np.array_equal(p1[0].reshape(-1, 2)[int(ok.sum()):], expect)
