@@ -43,6 +43,17 @@ def test_struct_layouts_match_header(tmp_path):
                      ctypes.sizeof(_lib.McSums), ctypes.sizeof(_lib.PairCfg)]
     assert sizes[0] == _lib.IMU_DTYPE.itemsize and sizes[1] == _lib.RESULT_DTYPE.itemsize
     assert sizes[3] == _lib.MCSUMS_DTYPE.itemsize
+    # tracker structs: sizes and the offsets of the fields that follow padding
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ofb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(ofb_tracker_cfg),sizeof(ofb_track_result),offsetof(ofb_tracker_cfg,n_streams),'
+                   'offsetof(ofb_tracker_cfg,max_speed),offsetof(ofb_tracker_cfg,gate_T),offsetof(ofb_tracker_cfg,borrow_frames),'
+                   'offsetof(ofb_track_result,n_points));return 0;}\n')
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    t = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    T, R = _lib.TrackerCfg, _lib.TrackResult
+    assert t == [ctypes.sizeof(T), ctypes.sizeof(R), T.n_streams.offset, T.max_speed.offset, T.gate_T.offset,
+                 T.borrow_frames.offset, R.n_points.offset]
+    assert t[1] == _lib.TRACK_RESULT_DTYPE.itemsize and t[6] == _lib.TRACK_RESULT_DTYPE.fields["n_points"][1]
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode")
