@@ -34,6 +34,16 @@ struct ofb_tracker {
     int pcur = 0;
     DevBuf counts;                     // int [3][S]: count, need (top-up flag), kept (count after the gates)
     DevBuf nxt, status, err, kept_prev, det, vlast, mask, hw, bgr;
+    // CUDA-graph replay of the steady-state step for small fleets fed from host memory (the launch-bound case: a
+    // step is ~15 tiny launches/copies). Inputs are staged in pinned buffers at fixed addresses, so one captured
+    // graph per ping-pong parity (x with/without v_prior) serves every later step.
+    PinBuf pin_in, pin_out;
+    DevBuf dev_io;                     // imu | v_prior | results
+    cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    uint64_t glaunches[2][2] = {{0, 0}, {0, 0}};
+    bool graph_ok = true;
+    int plain_steps = 0;               // steps run launch by launch since creation (scratch arenas are sized by them)
+    uint64_t graph_steps = 0;
 };
 
 namespace {
@@ -346,7 +356,10 @@ extern "C" int ofb_tracker_destroy(ofb_tracker* t)
         if (t->pyr[i]) { cudaFree(t->pyr[i]->base); delete t->pyr[i]; }
         t->frames[i].release(); t->pts[i].release();
     }
-    DevBuf* bufs[] = {&t->counts, &t->nxt, &t->status, &t->err, &t->kept_prev, &t->det, &t->vlast, &t->mask, &t->hw, &t->bgr};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) if (t->gexec[i][j]) cudaGraphExecDestroy(t->gexec[i][j]);
+    t->pin_in.release(); t->pin_out.release();
+    DevBuf* bufs[] = {&t->counts, &t->nxt, &t->status, &t->err, &t->kept_prev, &t->det, &t->vlast, &t->mask, &t->hw, &t->bgr, &t->dev_io};
     for (DevBuf* b : bufs) b->release();
     delete t;
     return OFB_OK;
@@ -384,19 +397,15 @@ extern "C" int ofb_tracker_set_points(ofb_tracker* t, const float* pts, const in
     return OFB_OK;
 }
 
-extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch, size_t image_stride,
-                                const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
-                                float* pts_out, int* n_out, float* kept_prev, float* kept_next)
+// One step, launch by launch, on ctx->stream (also the body that is captured into a graph).
+static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitch, size_t image_stride,
+                                 const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
+                                 float* pts_out, int* n_out, float* kept_prev, float* kept_next)
 {
-    OFB_REQUIRE(t && frames && imu && results, "tracker_step: null argument");
     ofb_ctx* ctx = t->ctx;
     const ofb_tracker_cfg& cfg = t->cfg;
     const ofb_pair_cfg& pc = cfg.pair;
     const int S = cfg.n_streams, w = pc.width, h = pc.height, K = pc.max_corners, cap = t->cap;
-    const int bpp = cfg.bgr_input ? 3 : 1;
-    OFB_REQUIRE(pitch >= bpp * w, "tracker_step: pitch smaller than a row");
-    OFB_REQUIRE(S == 1 || image_stride >= (size_t)pitch * (h - 1) + (size_t)bpp * w, "tracker_step: image_stride too small");
-    OFB_CUDA(cudaSetDevice(ctx->device));
     const size_t np = (size_t)S * cap;
     OutStage o[2];
     OFB_TRY(ofb_stage_out(ctx, SC_OUT3, results, sizeof(ofb_track_result) * S, &o[0]));
@@ -488,6 +497,97 @@ extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch
     int rc = ofb_finish_out(ctx, o, 2);
     if (rc == OFB_OK && host_out) OFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+// Steady-state step replayed from a captured CUDA graph. Returns OFB_E_UNSUPPORTED when the graph could not be
+// built (the caller then runs the step launch by launch; nothing has executed and the tracker state is unchanged).
+static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, size_t image_stride,
+                              const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results)
+{
+    ofb_ctx* ctx = t->ctx;
+    const int S = t->cfg.n_streams, w = t->cfg.pair.width, h = t->cfg.pair.height;
+    const size_t row = (size_t)(t->cfg.bgr_input ? 3 : 1) * w, fbytes = row * h;
+    const size_t off_imu = (fbytes * S + 255) & ~(size_t)255, off_vp = off_imu + sizeof(ofb_imu_sample) * S;
+    const size_t in_bytes = off_vp + sizeof(double) * 3 * S;
+    const size_t d_vp = sizeof(ofb_imu_sample) * S, d_res = d_vp + sizeof(double) * 3 * S;
+    if (!t->pin_in.p) {                 // fixed sizes: allocated once, the addresses are baked into the graphs
+        OFB_TRY(t->pin_in.reserve(in_bytes));
+        OFB_TRY(t->pin_out.reserve(sizeof(ofb_track_result) * S));
+        OFB_TRY(t->dev_io.reserve(d_res + sizeof(ofb_track_result) * S));
+    }
+    uint8_t* pin = (uint8_t*)t->pin_in.p;
+    uint8_t* dio = t->dev_io.as<uint8_t>();
+    for (int s = 0; s < S; ++s) {
+        const uint8_t* src = frames + (size_t)s * image_stride;
+        if ((size_t)pitch == row) memcpy(pin + (size_t)s * fbytes, src, fbytes);
+        else for (int y = 0; y < h; ++y) memcpy(pin + (size_t)s * fbytes + (size_t)y * row, src + (size_t)y * pitch, row);
+    }
+    memcpy(pin + off_imu, imu, sizeof(ofb_imu_sample) * S);
+    if (v_prior) memcpy(pin + off_vp, v_prior, sizeof(double) * 3 * S);
+    const int par = t->cur, hp = v_prior ? 1 : 0;
+    if (!t->gexec[par][hp]) {
+        // capture = a dry run of the launch-by-launch body: it advances the host-side ping-pong state, which is
+        // restored afterwards (the graph launch below is what executes the step)
+        const int cur0 = t->cur, pcur0 = t->pcur; const bool hp0 = t->have_prev; const uint64_t l0 = ctx->launches;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return OFB_E_UNSUPPORTED; }
+        int rc = OFB_OK;
+        if (cudaMemcpyAsync(dio, pin + off_imu, sizeof(ofb_imu_sample) * S, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
+        if (rc == OFB_OK && v_prior &&
+            cudaMemcpyAsync(dio + d_vp, pin + off_vp, sizeof(double) * 3 * S, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
+        if (rc == OFB_OK)
+            rc = tracker_step_launches(t, pin, (int)row, fbytes, (const ofb_imu_sample*)dio, v_prior ? (const double*)(dio + d_vp) : nullptr,
+                                       (ofb_track_result*)(dio + d_res), nullptr, nullptr, nullptr, nullptr);
+        if (rc == OFB_OK && cudaMemcpyAsync(t->pin_out.p, dio + d_res, sizeof(ofb_track_result) * S, cudaMemcpyDeviceToHost,
+                                            ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        const uint64_t captured = ctx->launches - l0;
+        t->cur = cur0; t->pcur = pcur0; t->have_prev = hp0; ctx->launches = l0;
+        if (rc != OFB_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return OFB_E_UNSUPPORTED; }
+        cudaGraphExec_t ex = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess || !ex) { cudaGetLastError(); return OFB_E_UNSUPPORTED; }
+        t->gexec[par][hp] = ex; t->glaunches[par][hp] = captured;
+    }
+    OFB_CUDA(cudaGraphLaunch(t->gexec[par][hp], ctx->stream));
+    ctx->launches += t->glaunches[par][hp];
+    t->pcur ^= 1; t->cur ^= 1; t->graph_steps++;
+    OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(results, t->pin_out.p, sizeof(ofb_track_result) * S);
+    return OFB_OK;
+}
+
+extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch, size_t image_stride,
+                                const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
+                                float* pts_out, int* n_out, float* kept_prev, float* kept_next)
+{
+    OFB_REQUIRE(t && frames && imu && results, "tracker_step: null argument");
+    ofb_ctx* ctx = t->ctx;
+    const int S = t->cfg.n_streams, w = t->cfg.pair.width, h = t->cfg.pair.height, bpp = t->cfg.bgr_input ? 3 : 1;
+    OFB_REQUIRE(pitch >= bpp * w, "tracker_step: pitch smaller than a row");
+    OFB_REQUIRE(S == 1 || image_stride >= (size_t)pitch * (h - 1) + (size_t)bpp * w, "tracker_step: image_stride too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    // launch-bound case (a few small frames from host memory, only the result records wanted): replay a graph
+    const char* genv = getenv("OFB_TRACKER_GRAPH");
+    const bool graphs_on = !(genv && genv[0] == '0');
+    if (graphs_on && t->graph_ok && t->have_prev && t->plain_steps >= 3 && !pts_out && !n_out && !kept_prev && !kept_next &&
+        (size_t)S * bpp * w * h <= ((size_t)16 << 20) && !ofb_is_device_ptr(frames) && !ofb_is_device_ptr(imu) &&
+        !ofb_is_device_ptr(results) && !(v_prior && ofb_is_device_ptr(v_prior))) {
+        const int rc = tracker_step_graph(t, frames, pitch, image_stride, imu, v_prior, results);
+        if (rc != OFB_E_UNSUPPORTED) return rc;
+        t->graph_ok = false;            // this build / driver cannot capture the step: stay on plain launches
+    }
+    t->plain_steps++;
+    return tracker_step_launches(t, frames, pitch, image_stride, imu, v_prior, results, pts_out, n_out, kept_prev, kept_next);
+}
+
+/* number of steps replayed from a CUDA graph so far (0 when graphs are off or were never eligible) */
+extern "C" int ofb_tracker_graph_steps(const ofb_tracker* t, uint64_t* out)
+{
+    OFB_REQUIRE(t && out, "tracker_graph_steps: null argument");
+    *out = t->graph_steps;
+    return OFB_OK;
 }
 
 extern "C" int ofb_tracker_render_mask(ofb_ctx* ctx, const float* pts, int n, int radius, int w, int h, uint8_t* mask_out)

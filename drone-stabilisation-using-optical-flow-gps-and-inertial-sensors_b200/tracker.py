@@ -79,6 +79,12 @@ class StreamTracker:
         except Exception:
             pass
 
+    def graph_steps(self):
+        """steps replayed from a captured CUDA graph so far (small fleets fed from host memory; include/ofb200.h)"""
+        n = C.c_uint64()
+        _lib.check(self.ctx.lib.ofb_tracker_graph_steps(self.h, C.byref(n)))
+        return n.value
+
     def reset(self):
         _lib.check(self.ctx.lib.ofb_tracker_reset(self.h))
 

@@ -260,6 +260,11 @@ int ofb_tracker_set_points(ofb_tracker* trk, const float* pts, const int* counts
 int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t image_stride,
                      const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
                      float* pts_out, int* n_out, float* kept_prev, float* kept_next);
+/* Small fleets fed from host memory (<= 16 MB of frames per step, host imu/results, no optional outputs) are
+ * launch bound: from the fourth step on such a step is replayed from a captured CUDA graph (inputs staged in
+ * pinned buffers at fixed addresses; one graph per ping-pong parity). Results are identical to the launch-by-launch
+ * path; OFB_TRACKER_GRAPH=0 in the environment disables it. *steps_out = steps replayed from a graph so far. */
+int ofb_tracker_graph_steps(const ofb_tracker* trk, uint64_t* steps_out);
 /* the exclusion mask OFB_TOPUP_APPEND_MASKED would use for `n` points (n x 2 float32): mask_out h x w u8
  * (1 = allowed, 0 = inside a circle). Exposed for parity tests against cv2.circle. */
 int ofb_tracker_render_mask(ofb_ctx* ctx, const float* pts, int n, int radius, int w, int h, uint8_t* mask_out);

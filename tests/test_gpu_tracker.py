@@ -315,3 +315,40 @@ def test_initialize_ft_as_intended(ofb200, ctx):
     assert len(h) == len(he) == len(pos) == len(perr) and 10 <= len(h) <= 40
     assert np.all(np.diff(he) >= 0), "eval_ft with weight on the height error sorts by it"
     assert np.abs(np.median(np.abs(h)) - Z) < 0.5 * Z
+
+
+@pytest.mark.parametrize("name", ["exp", "node", "module"])
+def test_graph_replay_equals_plain_launches(ofb200, ctx, name, monkeypatch):
+    """Small fleets fed from host memory replay the steady-state step from a captured CUDA graph (include/ofb200.h,
+    ofb_tracker_graph_steps). Results and the device-resident point sets are identical to the launch-by-launch path
+    (OFB_TRACKER_GRAPH=0), including steps whose top-up fires inside the graph."""
+    frames, imus, kw = tc.build(name)
+    S, T = len(frames), len(frames[0])
+    # a longer run: the sequence forwards, then backwards
+    order = list(range(T)) + list(range(T - 2, -1, -1))
+
+    def run(graph):
+        monkeypatch.setenv("OFB_TRACKER_GRAPH", "1" if graph else "0")
+        trk = make_gpu_tracker(ofb200, ctx, kw, S)
+        out = []
+        try:
+            for k in order:
+                samples = [imus[s][k] for s in range(S)]
+                fr = np.stack([frames[s][k] for s in range(S)])
+                out.append(trk.step(fr, imu_records(ofb200, samples), v_prior=priors(samples)).copy())
+            n_graph = trk.graph_steps()
+            res, pts = trk.step(np.stack([frames[s][1] for s in range(S)]), imu_records(ofb200, [imus[s][1] for s in range(S)]),
+                                v_prior=priors([imus[s][1] for s in range(S)]), want_points=True)
+            out.append(res.copy())
+        finally:
+            trk.close()
+        return out, pts, n_graph
+    plain, ppts, n0 = run(False)
+    graph, gpts, n1 = run(True)
+    assert n0 == 0 and n1 == len(order) - 3, (n0, n1)      # the first three steps size the scratch arenas
+    assert sum(int((r["n_added"] > 0).sum()) for r in graph[3:]) >= 1, "no top-up inside a graph step: weak test"
+    for k, (a, b) in enumerate(zip(plain, graph)):
+        for s in range(S):
+            assert same_record(a[s], b[s]), "step %d stream %d" % (k, s)
+    for s in range(S):
+        assert np.array_equal(ppts[s], gpts[s])
