@@ -120,7 +120,7 @@ _SIGNATURES = {
     "ofb_tracker_capacity": (i32, [vp, C.POINTER(i32)]),
     "ofb_tracker_set_points": (i32, [vp, vp, vp]),
     "ofb_tracker_step": (i32, [vp, vp, i32, sz, vp, vp, vp, vp, vp, vp, vp]),
-    "ofb_tracker_graph_steps": (i32, [vp, C.POINTER(u64)]),
+    "ofb_tracker_graph_info": (i32, [vp, C.POINTER(u64), C.POINTER(i32)]),
     "ofb_tracker_render_mask": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ofb_mc_sweep": (i32, [vp, vp, i32, i32, vp, vp, i32, u64, u64, u64, i32, vp, vp, vp]),
     "ofb_mc_feas": (i32, [vp, vp, i32, vp, vp, u64, u64, u64, vp]),

@@ -42,6 +42,9 @@ struct ofb_tracker {
     cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint64_t glaunches[2][2] = {{0, 0}, {0, 0}};
     bool graph_ok = true;
+    bool cond_ok = true;               // the top-up path may sit in a conditional (IF) node of the graph (opt-in)
+    bool capturing = false, capture_cond = false, cond_used = false;
+    cudaStream_t side_stream = nullptr;   // captures the body of the conditional node
     int plain_steps = 0;               // steps run launch by launch since creation (scratch arenas are sized by them)
     uint64_t graph_steps = 0;
 };
@@ -58,6 +61,7 @@ struct TrackerDev {
     double max_speed, dummy; int gate_mode; double gate_T;
     int min_solve, min_features, topup_mode, max_features;
     int have_prev;
+    int use_cond; cudaGraphConditionalHandle cond;                  // graph replay: switch the top-up branch on
 };
 
 struct KeptLoader {
@@ -169,6 +173,7 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         out[s] = r;
         if (solve) { T.vlast[3 * s] = o.v[0]; T.vlast[3 * s + 1] = o.v[1]; T.vlast[3 * s + 2] = o.v[2]; }
         const int need = kept <= T.min_features;
+        if (need && T.use_cond) cudaGraphSetConditional(T.cond, 1u);  // any stream that needs a top-up enables the branch
         T.kept[s] = kept;
         T.need[s] = need;
         T.count[s] = (need && T.topup_mode == OFB_TOPUP_REPLACE) ? 0 : kept;    // of_module.py:86 replaces the set
@@ -359,6 +364,7 @@ extern "C" int ofb_tracker_destroy(ofb_tracker* t)
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j) if (t->gexec[i][j]) cudaGraphExecDestroy(t->gexec[i][j]);
     t->pin_in.release(); t->pin_out.release();
+    if (t->side_stream) cudaStreamDestroy(t->side_stream);
     DevBuf* bufs[] = {&t->counts, &t->nxt, &t->status, &t->err, &t->kept_prev, &t->det, &t->vlast, &t->mask, &t->hw, &t->bgr, &t->dev_io};
     for (DevBuf* b : bufs) b->release();
     delete t;
@@ -455,6 +461,20 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     T.max_speed = cfg.max_speed; T.dummy = cfg.dummy_value; T.gate_mode = cfg.gate_mode; T.gate_T = cfg.gate_T;
     T.min_solve = cfg.min_solve; T.min_features = cfg.min_features; T.topup_mode = cfg.topup_mode; T.max_features = K;
     T.have_prev = t->have_prev ? 1 : 0;
+    // graph capture: the top-up path goes into the body of an IF node whose condition the filter kernel sets, so a
+    // steady-state replay does not even launch the five kernels and two memsets that would exit at once
+    T.use_cond = 0; T.cond = 0;
+    cudaGraph_t cap_graph = nullptr;
+    if (t->capturing && t->capture_cond) {
+        cudaStreamCaptureStatus cs; const cudaGraphNode_t* deps = nullptr; size_t nd = 0;
+        if (cudaStreamGetCaptureInfo_v2(ctx->stream, &cs, nullptr, &cap_graph, &deps, &nd) != cudaSuccess ||
+            cs != cudaStreamCaptureStatusActive ||
+            cudaGraphConditionalHandleCreate(&T.cond, cap_graph, 0, cudaGraphCondAssignDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return OFB_E_UNSUPPORTED;
+        }
+        T.use_cond = 1;
+    }
     // 2. track the stream's points from the kept frame into the new one
     if (t->have_prev)
         OFB_TRY(ofb_lk_device(ctx, t->pyr[t->cur ^ 1], 0, 1, t->pyr[t->cur], 0, 1, S, P, count, 1, cap, (size_t)cap, pc.win_w,
@@ -474,10 +494,40 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     OFB_TRY(copy_out(kept_prev, t->kept_prev.as<float>()));
     OFB_TRY(copy_out(kept_next, Pn));                                 // the head of the new point set, before any top-up
     // 5. top-up on the current frame; streams that do not need it are skipped inside the kernels (no host sync)
+    cudaStream_t main_stream = ctx->stream;
+    cudaGraphNode_t cond_node = nullptr;
+    if (T.use_cond) {
+        cudaStreamCaptureStatus cs; const cudaGraphNode_t* deps = nullptr; size_t nd = 0;
+        cudaGraphNodeParams gp = {};
+        gp.type = cudaGraphNodeTypeConditional;
+        gp.conditional.handle = T.cond; gp.conditional.type = cudaGraphCondTypeIf; gp.conditional.size = 1;
+        if (cudaStreamGetCaptureInfo_v2(main_stream, &cs, nullptr, &cap_graph, &deps, &nd) != cudaSuccess ||
+            cudaGraphAddNode(&cond_node, cap_graph, deps, nd, &gp) != cudaSuccess || !gp.conditional.phGraph_out ||
+            cudaStreamBeginCaptureToGraph(t->side_stream, gp.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                          cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return OFB_E_UNSUPPORTED;
+        }
+        ctx->stream = t->side_stream;                                 // the top-up launches below land in the IF body
+    }
+    auto end_body = [&](int rc) -> int {
+        if (!T.use_cond) return rc;
+        ctx->stream = main_stream;
+        cudaGraph_t body = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(t->side_stream, &body);
+        if (rc != OFB_OK) { cudaGetLastError(); return rc; }
+        if (e != cudaSuccess ||
+            cudaStreamUpdateCaptureDependencies(main_stream, &cond_node, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) {
+            cudaGetLastError();
+            return OFB_E_UNSUPPORTED;
+        }
+        return OFB_OK;
+    };
     const uint8_t* mask = nullptr;
     if (cfg.topup_mode == OFB_TOPUP_APPEND_MASKED && cfg.mask_radius > 0) {
-        OFB_TRY(render_mask_device(ctx, t->mask.as<uint8_t>(), w, h, t->pitch_d, t->stride_d, S, Pn, (size_t)cap, cap, count, need,
-                                   t->hw.as<int>(), cfg.mask_radius));
+        const int mr = render_mask_device(ctx, t->mask.as<uint8_t>(), w, h, t->pitch_d, t->stride_d, S, Pn, (size_t)cap, cap, count,
+                                          need, t->hw.as<int>(), cfg.mask_radius);
+        if (mr != OFB_OK) return end_body(mr);
         mask = t->mask.as<uint8_t>();
     }
     FeatImageState* st = nullptr;
@@ -486,9 +536,14 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     int fr = ofb_features_device(ctx, f, w, h, fpitch, (S == 1 ? 0 : fstride), S, mask, t->pitch_d, t->stride_d, K, pc.quality,
                                  pc.min_distance, pc.block_size, cand_cap, t->det.as<float>(), (size_t)2 * K, K, &st);
     ctx->feat_active = nullptr;
-    OFB_TRY(fr);
+    if (fr != OFB_OK) return end_body(fr);
     topup_append_kernel<<<S, 128, 0, ctx->stream>>>(T, st, t->det.as<float>(), Pn, (ofb_track_result*)o[0].dev);
-    OFB_LAUNCH_CHECK(ctx);
+    ctx->launches++;
+    {
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { ofb_set_error("tracker_step: topup_append launch -> %s", cudaGetErrorString(le)); return end_body(OFB_E_CUDA); }
+    }
+    OFB_TRY(end_body(OFB_OK));
     if (o[1].dev) OFB_CUDA(cudaMemcpyAsync(o[1].dev, count, sizeof(int) * S, cudaMemcpyDeviceToDevice, ctx->stream));
     OFB_TRY(copy_out(pts_out, Pn));
     t->pcur ^= 1;
@@ -525,13 +580,19 @@ static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, 
     memcpy(pin + off_imu, imu, sizeof(ofb_imu_sample) * S);
     if (v_prior) memcpy(pin + off_vp, v_prior, sizeof(double) * 3 * S);
     const int par = t->cur, hp = v_prior ? 1 : 0;
-    if (!t->gexec[par][hp]) {
+    if (!t->side_stream) OFB_CUDA(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+    for (int attempt = 0; attempt < 2 && !t->gexec[par][hp]; ++attempt) {
         // capture = a dry run of the launch-by-launch body: it advances the host-side ping-pong state, which is
         // restored afterwards (the graph launch below is what executes the step)
         const int cur0 = t->cur, pcur0 = t->pcur; const bool hp0 = t->have_prev; const uint64_t l0 = ctx->launches;
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return OFB_E_UNSUPPORTED; }
         int rc = OFB_OK;
+        // OFB_TRACKER_COND=1 puts the top-up path into a conditional node. Measured on B200 (640x480, 200 features): the
+        // IF node costs more (97 us per step) than the seven nodes it skips, which exit at once (93 us) -- so the
+        // default keeps them inline.
+        const char* ce = getenv("OFB_TRACKER_COND");
+        t->capturing = true; t->capture_cond = t->cond_ok && ce && ce[0] == '1';
         if (cudaMemcpyAsync(dio, pin + off_imu, sizeof(ofb_imu_sample) * S, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
         if (rc == OFB_OK && v_prior &&
             cudaMemcpyAsync(dio + d_vp, pin + off_vp, sizeof(double) * 3 * S, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
@@ -542,14 +603,22 @@ static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, 
                                             ctx->stream) != cudaSuccess) rc = OFB_E_CUDA;
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         const uint64_t captured = ctx->launches - l0;
+        const bool with_cond = t->capture_cond;
+        t->capturing = false; t->capture_cond = false;
         t->cur = cur0; t->pcur = pcur0; t->have_prev = hp0; ctx->launches = l0;
-        if (rc != OFB_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return OFB_E_UNSUPPORTED; }
         cudaGraphExec_t ex = nullptr;
-        const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
-        cudaGraphDestroy(g);
-        if (ei != cudaSuccess || !ex) { cudaGetLastError(); return OFB_E_UNSUPPORTED; }
+        bool ok = rc == OFB_OK && e == cudaSuccess && g;
+        if (ok) ok = cudaGraphInstantiate(&ex, g, 0) == cudaSuccess && ex;
+        if (g) cudaGraphDestroy(g);
+        if (!ok) {
+            cudaGetLastError();
+            if (with_cond) { t->cond_ok = false; continue; }         // retry with the top-up path inline
+            return OFB_E_UNSUPPORTED;
+        }
         t->gexec[par][hp] = ex; t->glaunches[par][hp] = captured;
+        if (with_cond) t->cond_used = true;
     }
+    if (!t->gexec[par][hp]) return OFB_E_UNSUPPORTED;
     OFB_CUDA(cudaGraphLaunch(t->gexec[par][hp], ctx->stream));
     ctx->launches += t->glaunches[par][hp];
     t->pcur ^= 1; t->cur ^= 1; t->graph_steps++;
@@ -582,11 +651,13 @@ extern "C" int ofb_tracker_step(ofb_tracker* t, const uint8_t* frames, int pitch
     return tracker_step_launches(t, frames, pitch, image_stride, imu, v_prior, results, pts_out, n_out, kept_prev, kept_next);
 }
 
-/* number of steps replayed from a CUDA graph so far (0 when graphs are off or were never eligible) */
-extern "C" int ofb_tracker_graph_steps(const ofb_tracker* t, uint64_t* out)
+/* steps replayed from a CUDA graph so far (0 when graphs are off or were never eligible); *conditional_out = 1 when
+ * the top-up path sits in a conditional node of those graphs */
+extern "C" int ofb_tracker_graph_info(const ofb_tracker* t, uint64_t* steps_out, int* conditional_out)
 {
-    OFB_REQUIRE(t && out, "tracker_graph_steps: null argument");
-    *out = t->graph_steps;
+    OFB_REQUIRE(t && steps_out, "tracker_graph_info: null argument");
+    *steps_out = t->graph_steps;
+    if (conditional_out) *conditional_out = t->cond_used ? 1 : 0;
     return OFB_OK;
 }
 

@@ -81,9 +81,13 @@ class StreamTracker:
 
     def graph_steps(self):
         """steps replayed from a captured CUDA graph so far (small fleets fed from host memory; include/ofb200.h)"""
-        n = C.c_uint64()
-        _lib.check(self.ctx.lib.ofb_tracker_graph_steps(self.h, C.byref(n)))
-        return n.value
+        return self.graph_info()[0]
+
+    def graph_info(self):
+        """(steps replayed from a graph, whether the top-up path is a conditional node of it)"""
+        n, c = C.c_uint64(), C.c_int()
+        _lib.check(self.ctx.lib.ofb_tracker_graph_info(self.h, C.byref(n), C.byref(c)))
+        return n.value, bool(c.value)
 
     def reset(self):
         _lib.check(self.ctx.lib.ofb_tracker_reset(self.h))

@@ -263,8 +263,11 @@ int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t 
 /* Small fleets fed from host memory (<= 16 MB of frames per step, host imu/results, no optional outputs) are
  * launch bound: from the fourth step on such a step is replayed from a captured CUDA graph (inputs staged in
  * pinned buffers at fixed addresses; one graph per ping-pong parity). Results are identical to the launch-by-launch
- * path; OFB_TRACKER_GRAPH=0 in the environment disables it. *steps_out = steps replayed from a graph so far. */
-int ofb_tracker_graph_steps(const ofb_tracker* trk, uint64_t* steps_out);
+ * path; OFB_TRACKER_GRAPH=0 in the environment disables the graph. With OFB_TRACKER_COND=1 the top-up path becomes the
+ * body of a conditional (IF) node whose condition the filter kernel sets on the device (cudaGraphSetConditional);
+ * measured slower than letting its kernels exit at once, hence opt-in. *steps_out = steps replayed from a graph so
+ * far; *conditional_out (may be NULL) = 1 when those graphs use the conditional node. */
+int ofb_tracker_graph_info(const ofb_tracker* trk, uint64_t* steps_out, int* conditional_out);
 /* the exclusion mask OFB_TOPUP_APPEND_MASKED would use for `n` points (n x 2 float32): mask_out h x w u8
  * (1 = allowed, 0 = inside a circle). Exposed for parity tests against cv2.circle. */
 int ofb_tracker_render_mask(ofb_ctx* ctx, const float* pts, int n, int radius, int w, int h, uint8_t* mask_out);

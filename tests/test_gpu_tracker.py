@@ -327,8 +327,9 @@ def test_graph_replay_equals_plain_launches(ofb200, ctx, name, monkeypatch):
     # a longer run: the sequence forwards, then backwards
     order = list(range(T)) + list(range(T - 2, -1, -1))
 
-    def run(graph):
+    def run(graph, cond=True):
         monkeypatch.setenv("OFB_TRACKER_GRAPH", "1" if graph else "0")
+        monkeypatch.setenv("OFB_TRACKER_COND", "1" if cond else "0")
         trk = make_gpu_tracker(ofb200, ctx, kw, S)
         out = []
         try:
@@ -336,7 +337,7 @@ def test_graph_replay_equals_plain_launches(ofb200, ctx, name, monkeypatch):
                 samples = [imus[s][k] for s in range(S)]
                 fr = np.stack([frames[s][k] for s in range(S)])
                 out.append(trk.step(fr, imu_records(ofb200, samples), v_prior=priors(samples)).copy())
-            n_graph = trk.graph_steps()
+            n_graph = trk.graph_info()
             res, pts = trk.step(np.stack([frames[s][1] for s in range(S)]), imu_records(ofb200, [imus[s][1] for s in range(S)]),
                                 v_prior=priors([imus[s][1] for s in range(S)]), want_points=True)
             out.append(res.copy())
@@ -344,11 +345,13 @@ def test_graph_replay_equals_plain_launches(ofb200, ctx, name, monkeypatch):
             trk.close()
         return out, pts, n_graph
     plain, ppts, n0 = run(False)
-    graph, gpts, n1 = run(True)
-    assert n0 == 0 and n1 == len(order) - 3, (n0, n1)      # the first three steps size the scratch arenas
+    graph, gpts, n1 = run(True, cond=False)
+    inline, ipts, n2 = run(True, cond=True)              # opt-in: top-up path as a conditional node
+    assert n0 == (0, False) and n1 == (len(order) - 3, False) and n2[0] == len(order) - 3, (n0, n1, n2)   # three plain steps first
+    print("conditional top-up node in use:", n2[1])
     assert sum(int((r["n_added"] > 0).sum()) for r in graph[3:]) >= 1, "no top-up inside a graph step: weak test"
-    for k, (a, b) in enumerate(zip(plain, graph)):
+    for k, (a, b, c) in enumerate(zip(plain, graph, inline)):
         for s in range(S):
-            assert same_record(a[s], b[s]), "step %d stream %d" % (k, s)
+            assert same_record(a[s], b[s]) and same_record(a[s], c[s]), "step %d stream %d" % (k, s)
     for s in range(S):
-        assert np.array_equal(ppts[s], gpts[s])
+        assert np.array_equal(ppts[s], gpts[s]) and np.array_equal(ppts[s], ipts[s])

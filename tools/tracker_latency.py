@@ -30,7 +30,7 @@ trk = ofb200.StreamTracker(w, h, **kw)
 lat = []
 for k in range(210):
     t0 = time.perf_counter(); r = trk.step(b if k & 1 else a, imu); lat.append((time.perf_counter() - t0) * 1e6)
-print("host numpy frames via StreamTracker.step: p50 %.1f us" % np.percentile(lat[10:], 50))
+print("host numpy frames via StreamTracker.step: p50 %.1f us" % np.percentile(lat[10:], 50), "graph info", trk.graph_info())
 pa = torch.from_numpy(a).pin_memory(); pb = torch.from_numpy(b).pin_memory()
 res = np.zeros(1, ofb200._lib.TRACK_RESULT_DTYPE)
 lat = []
