@@ -341,14 +341,20 @@ extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_
         R(t->hw, sizeof(int) * ((size_t)cfg->mask_radius + 1));
     }
     if (rc != OFB_OK) { ofb_tracker_destroy(t); return rc; }
+    cudaError_t ce = cudaSuccess;
     if (t->hw.p) {
         std::vector<int> hw;
         circle_half_widths(cfg->mask_radius, hw);
-        OFB_CUDA(cudaMemcpyAsync(t->hw.p, hw.data(), sizeof(int) * hw.size(), cudaMemcpyHostToDevice, ctx->stream));
-        OFB_CUDA(cudaStreamSynchronize(ctx->stream));                 // hw is a local
+        ce = cudaMemcpyAsync(t->hw.p, hw.data(), sizeof(int) * hw.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);      // hw is a local
     }
-    OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * S, ctx->stream));
-    OFB_CUDA(cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * S, ctx->stream));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * S, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * S, ctx->stream);
+    if (ce != cudaSuccess) {
+        ofb_set_error("tracker_create: %s", cudaGetErrorString(ce));
+        ofb_tracker_destroy(t);
+        return OFB_E_CUDA;
+    }
     *out = t;
     return OFB_OK;
 }

@@ -244,6 +244,8 @@ typedef struct {
     int    n_points;         /* count after the step */
 } ofb_track_result;
 
+/* The tracker works on ctx's stream and scratch arenas: use it from the thread that uses ctx, and destroy it before
+ * the context. */
 int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_tracker** out);
 int ofb_tracker_destroy(ofb_tracker* trk);
 /* forget the previous frame and all points: the next step detects */
