@@ -606,6 +606,44 @@ def main():
                    "max_abs_v_diff_vs_detect_mode": float(np.abs(res_k["v"] - res_t["v"]).max()),
                    "note": "track+solve of given points (pyramid, LK, solve; no detection), resident frames"}
 
+    # the same single stream the way the reference's loops consume it: one frame after the other through the
+    # device-resident feature lifecycle (ofb_tracker_step: pyramid of the new frame, LK from the kept frame, status
+    # filter, solve, masked top-up when fewer than half the features survive). Sequential by construction (frame k+1
+    # starts from the points frame k produced), so this is a latency chain, not a batch.
+    trk = ofb200.StreamTracker(W, H, max_features=K_FEAT, min_features=K_FEAT // 2,
+                               feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+                               lk_params=dict(winSize=WIN, maxLevel=MAX_LEVEL, criteria=CRIT), topup="node", mask_radius=30,
+                               variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
+                               flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), borrow_frames=True, ctx=ctx)
+    d_tres = torch.zeros((B + 1) * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    isz, rsz = ofb200._lib.IMU_DTYPE.itemsize, ofb200._lib.TRACK_RESULT_DTYPE.itemsize
+
+    def step_lifecycle():
+        for k in range(B + 1):              # frame k of the stream; pair k-1 = (frame k-1, frame k)
+            ofb200._lib.check(lib.ofb_tracker_step(trk.h, d_seq.data_ptr() + k * P, W, P, d_imu_seq.data_ptr() + max(k - 1, 0) * isz,
+                                                   None, d_tres.data_ptr() + k * rsz, None, None, None, None))
+    for _ in range(max(args.warmup // 2, 1)):
+        step_lifecycle()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_lifecycle()
+    ms_life = ctx.timer_stop()
+    barrier()
+    if dist is not None:
+        t = torch.tensor([ms_life], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_life = float(t.item())
+    res_l = np.zeros(B + 1, ofb200._lib.TRACK_RESULT_DTYPE)
+    ctx.memcpy(res_l, d_tres, res_l.nbytes)
+    trk.close()
+    lifecycle = {"value": world * (B + 1) * args.steps / (ms_life * 1e-3), "unit": "frames/s",
+                 "ms_per_frame": ms_life / (args.steps * (B + 1)), "min_tracked": int(res_l["n_tracked"][1:].min()),
+                 "topups_per_pass": int((res_l["n_added"][1:] > 0).sum()),
+                 "max_abs_v_error_vs_truth": float(max(np.abs(res_l["v"][k + 1] - pairs[(k // 2) % len(pairs)][2]["v"]).max()
+                                                       for k in range(0, B, 2) if res_l["flags"][k + 1] & 1)),
+                 "note": "one stream, frame after frame through ofb_tracker_step (sequential dependency: a latency chain)"}
+
     # per-stage durations (CUDA events between the kernels of the same call path)
     ctx.set_profile(True)
     for _ in range(3):                     # the profiled call path sizes its own scratch on first use
@@ -754,7 +792,7 @@ def main():
                            "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
                            "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "independent_pairs": independent, "track_solve": track_solve, "mc": mc,
+                "clocks": clocks, "independent_pairs": independent, "track_solve": track_solve, "lifecycle": lifecycle, "mc": mc,
                 "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
         print(json.dumps(line))
     if dist is not None:
