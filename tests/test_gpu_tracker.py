@@ -355,3 +355,50 @@ def test_graph_replay_equals_plain_launches(ofb200, ctx, name, monkeypatch):
             assert same_record(a[s], b[s]) and same_record(a[s], c[s]), "step %d stream %d" % (k, s)
     for s in range(S):
         assert np.array_equal(ppts[s], gpts[s]) and np.array_equal(ppts[s], ipts[s])
+
+
+@pytest.mark.parametrize("bgr", [False, True])
+def test_odd_geometry_matches_the_pair_path(ofb200, ctx, bgr):
+    """Width/height that are not multiples of 4 or 16 (staging pitch != row length, unaligned BGR rows), two streams,
+    enough steps to reach the graph replay: tracks and velocity equal ofb_frame_pairs on the same grey frames."""
+    import synth
+    w, h, K = 333, 247, 120
+    seq = []
+    for s in range(2):
+        big = synth.texture(h + 40, w + 40, 70 + s)
+        seq.append([np.ascontiguousarray(big[3 * k + s:3 * k + s + h, 2 * k:2 * k + w]) for k in range(6)])
+    col = [[tc._bgr(f, s) for f in seq[s]] for s in range(2)]
+    gray = [[io.bgr2gray(f) for f in col[s]] for s in range(2)] if bgr else seq
+    kw = dict(max_features=K, min_features=K // 4, topup="node", mask_radius=9, variant="node", scaling=1.0 / 270.0,
+              feature_params=dict(qualityLevel=0.02, minDistance=7, blockSize=3), bgr=bgr)
+    imu = np.zeros(2, ofb200._lib.IMU_DTYPE)
+    imu["d"], imu["n"] = [1.2, 2.0], [0.0, 0.0, 1.0]
+    trk = ofb200.StreamTracker(w, h, n_streams=2, ctx=ctx, **kw)
+    cfg = ofb200.make_pair_cfg(w, h, K, 0.02, 7, 3, (15, 15), 3, (3, 20, 0.03), variant="node", pos_scale=1.0 / 270.0,
+                               flow_scale=1.0 / 270.0, detect=False)
+    src = col if bgr else seq
+    try:
+        res, pts = trk.step(np.stack([src[0][0], src[1][0]]), imu, want_points=True)
+        for k in range(1, 6):
+            want = k in (1, 2)                       # later steps without optional outputs: graph replay
+            out = trk.step(np.stack([src[0][k], src[1][k]]), imu, want_points=want)
+            prev = np.zeros((2, K, 2), np.float32); n_in = np.zeros(2, np.int32)
+            for s in range(2):
+                n_in[s] = len(pts[s]); prev[s, :n_in[s]] = pts[s].reshape(-1, 2)
+            ref, pp, pn, st = ofb200.frame_pairs(np.stack([gray[0][k - 1], gray[1][k - 1]]), np.stack([gray[0][k], gray[1][k]]), imu,
+                                                 cfg, pts_in=prev, n_in=n_in, want_tracks=True, ctx=ctx)
+            res = out[0] if want else out
+            for s in range(2):
+                ok = st[s, :n_in[s]] == 1
+                assert int(res["n_tracked"][s]) == int(ok.sum()) and int(res["n_prev"][s]) == int(n_in[s])
+                assert np.abs(res["v"][s] - ref["v"][s]).max() <= 1e-12 * max(1.0, np.abs(ref["v"][s]).max())
+                if want:
+                    assert np.array_equal(out[1][s].reshape(-1, 2)[:int(ok.sum())], pn[s, :n_in[s]][ok])
+            if want:
+                pts = out[1]
+            else:                                    # keep following the chain through the pair path's own tracks
+                pts = [np.concatenate([pn[s, :n_in[s]][st[s, :n_in[s]] == 1]]) for s in range(2)]
+                assert all(int(res["n_added"][s]) == 0 for s in range(2)), "a top-up would need the point set back"
+        assert trk.graph_steps() >= 2
+    finally:
+        trk.close()
