@@ -100,7 +100,8 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int wtot[OFB_SOLVE_THREADS / 32];
     const ofb_imu_sample& im = imu[s];
-    const int n = T.count[s];                                         // first frame: seeded points (or none) carry over
+    const int n = min(max(T.count[s], 0), T.cap);                     // first frame: seeded points (or none) carry over
+                                                                      // (clamped: device-side counts are not validated)
     const size_t base = (size_t)s * T.cap;
     double vp[3];
     {
