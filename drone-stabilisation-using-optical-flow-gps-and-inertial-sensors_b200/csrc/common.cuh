@@ -93,6 +93,7 @@ struct ofb_ctx {
     cudaStream_t aux_stream = nullptr, aux2_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     const int* feat_active = nullptr;            // per-image flags (device): the lambda_min kernels skip images whose flag is 0
+    bool feat_prezeroed = false;                 // the caller reset the per-image state and cell grids of the next features call
     bool fork_after_eig = false;                 // ofb_features_device records ev_fork after the lambda_min launch
     // second context (own stream + scratch) that takes every other chunk of a resident ofb_frame_pairs batch
     ofb_ctx* twin = nullptr;

@@ -16,3 +16,6 @@ int ofb_features_device(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitc
                         const uint8_t* mask, int mpitch, size_t mstride, int max_corners, double quality,
                         double min_distance, int block_size, unsigned int cand_cap, float* xy_out, size_t xy_stride,
                         int out_cap, FeatImageState** state_out);
+
+int ofb_features_scratch(ofb_ctx* ctx, int w, int h, double min_distance, int n_images, FeatImageState** st_out,
+                         int** grid_out, size_t* cell_stride_out);

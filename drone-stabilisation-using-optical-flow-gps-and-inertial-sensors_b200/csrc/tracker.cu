@@ -12,7 +12,7 @@
 //   ingest_bgr_kernel        BGR8 -> grey straight into the tracker's level-0 buffer (cv2.cvtColor arithmetic)
 //   track_filter_solve_kernel one CTA per stream: ordered compaction of the surviving points (ballot + block
 //                            scan), the two gates, then the fp64 normal-equation solve on the kept points
-//   mask_fill_kernel / mask_circle_kernel  exclusion mask of the masked top-up, only for streams that need it
+//   mask_render_kernel       exclusion mask of the masked top-up (ones + filled circles), only for streams that need it
 //   topup_append_kernel      appends the first (max_features - count) detected corners (greedy selection has the
 //                            prefix property: the first m corners of a longer run are the run with maxCorners = m)
 #include "common.cuh"
@@ -41,6 +41,7 @@ struct ofb_tracker {
     DevBuf dev_io;                     // imu | v_prior | results
     cudaGraphExec_t gexec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint64_t glaunches[2][2] = {{0, 0}, {0, 0}};
+    uint64_t gsig[2][2] = {{0, 0}, {0, 0}};   // signature of the context's scratch arenas the graph's pointers refer to
     bool graph_ok = true;
     bool cond_ok = true;               // the top-up path may sit in a conditional (IF) node of the graph (opt-in)
     bool capturing = false, capture_cond = false, cond_used = false;
@@ -62,6 +63,7 @@ struct TrackerDev {
     int min_solve, min_features, topup_mode, max_features;
     int have_prev;
     int use_cond; cudaGraphConditionalHandle cond;                  // graph replay: switch the top-up branch on
+    FeatImageState* feat_state; int* cell_grid; size_t cell_stride; // detector scratch, reset here instead of by memsets
 };
 
 struct KeptLoader {
@@ -165,7 +167,12 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         KeptLoader ld{T.kept_prev, T.kept_next, kept, (size_t)T.cap, T.cx, T.cy, T.ps, T.fs};
         o = ofb_block_solve(ld, s, T.variant, im.d, im.n, im.w, im.t);
     }
+    // the detector's per-image state and (for streams that will top up) its min-distance cell grid start clean
+    if (kept <= T.min_features)
+        for (size_t i = tid; i < T.cell_stride; i += OFB_SOLVE_THREADS) T.cell_grid[(size_t)s * T.cell_stride + i] = -1;
     if (tid == 0) {
+        FeatImageState z; z.max_key = 0; z.n_cand = 0; z.n_out = 0; z.overflow = 0;
+        T.feat_state[s] = z;
         ofb_track_result r;
         for (int k = 0; k < 3; ++k) { r.v[k] = solve ? o.v[k] : 0.0; r.s[k] = solve ? o.s[k] : 0.0; }
         r.res = solve ? o.res : 0.0; r.rank = solve ? o.rank : 0;
@@ -210,37 +217,34 @@ __global__ void ingest_bgr_kernel(const uint8_t* __restrict__ bgr, int w, int h,
     else for (int k = 0; k < npx; ++k) g[k] = (o >> (8 * k)) & 255;
 }
 
-__global__ void mask_fill_kernel(uint8_t* __restrict__ mask, size_t mstride, const int* __restrict__ need)
-{
-    const int s = blockIdx.y;
-    if (need && !need[s]) return;
-    uint4* m = (uint4*)(mask + (size_t)s * mstride);
-    const size_t n16 = mstride / 16;                                  // mstride is a multiple of 256
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
-        m[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-}
-
-// cv2.circle(mask, (int(x), int(y)), radius, 0, FILLED): clipped union of the midpoint-circle spans; hw[|dy|] is the
-// half width of row cy+dy (computed once on the host from OpenCV's loop). MASK_CTAS CTAs per stream walk the points;
-// per point the warps take the rows and the lanes the bytes of a row (coalesced stores). Streams that need no top-up
-// cost one exiting CTA row.
-#define MASK_CTAS 8
+// Exclusion mask of the masked top-up: ones, with cv2.circle(mask, (int(x), int(y)), radius, 0, FILLED) at every
+// surviving point = the clipped union of the midpoint-circle spans; hw[|dy|] is the half width of row cy+dy (computed
+// once on the host from OpenCV's loop). MASK_CTAS CTAs per stream, each owning a band of rows: it fills its band
+// with ones, then draws the part of every circle that falls into the band (warps over points, lanes over the bytes
+// of a row) -- no ordering between CTAs is needed. Streams that need no top-up cost one exiting CTA row.
+#define MASK_CTAS 16
 __global__ void __launch_bounds__(256)
-mask_circle_kernel(uint8_t* __restrict__ mask, int w, int h, int mpitch, size_t mstride, const float* __restrict__ pts,
+mask_render_kernel(uint8_t* __restrict__ mask, int w, int h, int mpitch, size_t mstride, const float* __restrict__ pts,
                    size_t pts_stride, const int* __restrict__ count, const int* __restrict__ need,
                    const int* __restrict__ hw, int radius)
 {
     const int s = blockIdx.y;
     if (need && !need[s]) return;
-    const int n = count[s], lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int r0 = (int)((long long)blockIdx.x * h / gridDim.x), r1 = (int)((long long)(blockIdx.x + 1) * h / gridDim.x);
     uint8_t* m = mask + (size_t)s * mstride;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    {
+        uint4* band = (uint4*)(m + (size_t)r0 * mpitch);              // mpitch is a multiple of 16, mstride of 256
+        const size_t n16 = (size_t)(r1 - r0) * mpitch / 16;
+        for (size_t i = threadIdx.x; i < n16; i += blockDim.x) band[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    }
+    __syncthreads();
+    const int n = count ? count[s] : 0, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nwarps) {
         const float fx = pts[2 * ((size_t)s * pts_stride + i)], fy = pts[2 * ((size_t)s * pts_stride + i) + 1];
         const int cx = (int)fx, cy = (int)fy;                         // Python-2 cv2 truncates float coordinates
-        for (int r = warp; r <= 2 * radius; r += nwarps) {
-            const int dy = r - radius, y = cy + dy;
-            if (y < 0 || y >= h) continue;
-            const int half = hw[dy < 0 ? -dy : dy];
+        const int ya = max(cy - radius, r0), yb = min(cy + radius, r1 - 1);
+        for (int y = ya; y <= yb; ++y) {
+            const int dy = y - cy, half = hw[dy < 0 ? -dy : dy];
             const int x0 = max(cx - half, 0), x1 = min(cx + half, w - 1);
             for (int x = x0 + lane; x <= x1; x += 32) m[(size_t)y * mpitch + x] = 0;
         }
@@ -292,15 +296,10 @@ int render_mask_device(ofb_ctx* ctx, uint8_t* mask, int w, int h, int mpitch, si
                        const float* pts, size_t pts_stride, int max_pts, const int* count, const int* need, const int* hw,
                        int radius)
 {
-    const unsigned int fill_ctas = (unsigned int)((mstride / 16 + 255) / 256);
-    dim3 fg(fill_ctas < 16 ? fill_ctas : 16, n_streams);
-    mask_fill_kernel<<<fg, 256, 0, ctx->stream>>>(mask, mstride, need);
+    (void)max_pts;
+    dim3 grid(h < MASK_CTAS ? h : MASK_CTAS, n_streams);
+    mask_render_kernel<<<grid, 256, 0, ctx->stream>>>(mask, w, h, mpitch, mstride, pts, pts_stride, count, need, hw, radius);
     OFB_LAUNCH_CHECK(ctx);
-    if (max_pts > 0 && radius >= 0) {
-        dim3 cg(max_pts < MASK_CTAS ? max_pts : MASK_CTAS, n_streams);
-        mask_circle_kernel<<<cg, 256, 0, ctx->stream>>>(mask, w, h, mpitch, mstride, pts, pts_stride, count, need, hw, radius);
-        OFB_LAUNCH_CHECK(ctx);
-    }
     return OFB_OK;
 }
 
@@ -468,6 +467,7 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     T.max_speed = cfg.max_speed; T.dummy = cfg.dummy_value; T.gate_mode = cfg.gate_mode; T.gate_T = cfg.gate_T;
     T.min_solve = cfg.min_solve; T.min_features = cfg.min_features; T.topup_mode = cfg.topup_mode; T.max_features = K;
     T.have_prev = t->have_prev ? 1 : 0;
+    OFB_TRY(ofb_features_scratch(ctx, w, h, pc.min_distance, S, &T.feat_state, &T.cell_grid, &T.cell_stride));
     // graph capture: the top-up path goes into the body of an IF node whose condition the filter kernel sets, so a
     // steady-state replay does not even launch the five kernels and two memsets that would exit at once
     T.use_cond = 0; T.cond = 0;
@@ -540,9 +540,11 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     FeatImageState* st = nullptr;
     const unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
     ctx->feat_active = need;
+    ctx->feat_prezeroed = true;                                       // done by track_filter_solve_kernel
     int fr = ofb_features_device(ctx, f, w, h, fpitch, (S == 1 ? 0 : fstride), S, mask, t->pitch_d, t->stride_d, K, pc.quality,
                                  pc.min_distance, pc.block_size, cand_cap, t->det.as<float>(), (size_t)2 * K, K, &st);
     ctx->feat_active = nullptr;
+    ctx->feat_prezeroed = false;
     if (fr != OFB_OK) return end_body(fr);
     topup_append_kernel<<<S, 128, 0, ctx->stream>>>(T, st, t->det.as<float>(), Pn, (ofb_track_result*)o[0].dev);
     ctx->launches++;
@@ -559,6 +561,15 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     int rc = ofb_finish_out(ctx, o, 2);
     if (rc == OFB_OK && host_out) OFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+// The context's scratch arenas are shared with every other call on the context and grow on demand: a graph holds their
+// addresses, so it is rebuilt when any of them moved (another call needed a larger arena in between).
+static uint64_t scratch_signature(const ofb_ctx* ctx)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < OFB_NSCRATCH; ++i) { h ^= (uint64_t)(uintptr_t)ctx->scratch[i].p; h *= 1099511628211ull; }
+    return h;
 }
 
 // Steady-state step replayed from a captured CUDA graph. Returns OFB_E_UNSUPPORTED when the graph could not be
@@ -588,6 +599,10 @@ static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, 
     if (v_prior) memcpy(pin + off_vp, v_prior, sizeof(double) * 3 * S);
     const int par = t->cur, hp = v_prior ? 1 : 0;
     if (!t->side_stream) OFB_CUDA(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+    if (t->gexec[par][hp] && t->gsig[par][hp] != scratch_signature(ctx)) {
+        cudaGraphExecDestroy(t->gexec[par][hp]);
+        t->gexec[par][hp] = nullptr;
+    }
     for (int attempt = 0; attempt < 2 && !t->gexec[par][hp]; ++attempt) {
         // capture = a dry run of the launch-by-launch body: it advances the host-side ping-pong state, which is
         // restored afterwards (the graph launch below is what executes the step)
@@ -623,6 +638,7 @@ static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, 
             return OFB_E_UNSUPPORTED;
         }
         t->gexec[par][hp] = ex; t->glaunches[par][hp] = captured;
+        t->gsig[par][hp] = scratch_signature(ctx);                    // (the dry run cannot grow an arena: three plain steps sized them)
         if (with_cond) t->cond_used = true;
     }
     if (!t->gexec[par][hp]) return OFB_E_UNSUPPORTED;
