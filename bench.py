@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs generated (tiled to the batch)")
     ap.add_argument("--mc-trials", type=int, default=MC_TOTAL)
     ap.add_argument("--no-mc", action="store_true")
