@@ -62,7 +62,8 @@ class RosMessage(object):
 def _make_loader():
     import yaml
 
-    class Loader(yaml.SafeLoader):
+    # libyaml's C parser when PyYAML was built with it: the recordings are multi-megabyte files
+    class Loader(getattr(yaml, "CSafeLoader", yaml.SafeLoader)):
         pass
 
     def construct_new(loader, suffix, node):

@@ -94,10 +94,10 @@ def test_reference_recordings_load():
     assert np.all(np.diff(t) > 0) and 0.01 < np.median(np.diff(t)) < 0.05       # a ~47 Hz sonar
     assert 0.2 <= min(m.range for m in msgs) and max(m.range for m in msgs) <= 7.0
     tw = os.path.join(ref_loader.REF, "flight_experiments", "first_data", "vlsData.yaml")
-    with open(tw) as f:
-        head = "".join(f.readline() for _ in range(14 * 20))
-    tws = replay.load_ros_yaml(io.StringIO(head))
-    assert tws[0]._type == "TwistStamped" and tws[0].twist.linear._type == "Vector3" and tws[0].header.frame_id == "map"
+    tws = replay.load_ros_yaml(tw)                                      # the whole file (437 messages)
+    assert len(tws) > 400 and all(m._type == "TwistStamped" for m in tws)
+    assert tws[0].twist.linear._type == "Vector3" and tws[0].header.frame_id == "map"
+    assert np.all(np.diff(replay.stamps(tws)) >= 0)
 
 
 def test_velocity_kalman_equals_cv2():
