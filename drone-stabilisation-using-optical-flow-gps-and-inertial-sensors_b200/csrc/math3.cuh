@@ -80,9 +80,16 @@ OFB_HD void ofb_jacobi3(const double M[6], double ev[3], double q[3][3])
             for (int r = p + 1; r < 3; ++r) {
                 double apq = a[p][r];
                 if (apq == 0.0) continue;
-                double theta = (a[r][r] - a[p][p]) / (2.0 * apq);
-                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                // tan of the rotation angle, t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / (2 apq),
+                // multiplied through by |2 apq|: one square root and one division instead of two of each
+                const double d = a[r][r] - a[p][p], two = 2.0 * apq;
+                const double sg = (d == 0.0 || ((d > 0.0) == (apq > 0.0))) ? 1.0 : -1.0;
+                double t = sg * fabs(two) / (fabs(d) + sqrt(d * d + two * two));
+#ifdef __CUDA_ARCH__
+                double c = rsqrt(t * t + 1.0), s = t * c;
+#else
                 double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#endif
                 // A <- J^T A J
                 for (int k = 0; k < 3; ++k) {
                     double akp = a[k][p], akq = a[k][r];
