@@ -161,3 +161,68 @@ def exclusion_mask(points, radius, width, height, ctx=None):
     _lib.check(ctx.lib.ofb_tracker_render_mask(ctx.h, _lib.ptr(p) if len(p) else None, len(p), int(radius), int(width),
                                                int(height), _lib.ptr(m)))
     return m
+
+
+class FleetTracker:
+    """A fleet of camera streams sharded over the ranks of a torch.distributed group (stream s lives on
+    rank s mod world, no data-path collective). Every rank steps only its own streams through a local StreamTracker;
+    `gather_velocities` merges the per-stream velocities of the last step into one (n_streams, 3) table on every rank
+    with a single all-reduce (NCCL on the GPU box, gloo in the CPU tests).
+
+    tracker_factory(n_local_streams, **kw) builds the local tracker (default: StreamTracker on this rank's GPU)."""
+
+    def __init__(self, n_streams, width, height, group=None, tracker_factory=None, **tracker_kw):
+        import torch.distributed as dist
+        from .simulation import stream_shard
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_streams = int(n_streams)
+        self.streams = stream_shard(self.n_streams, self.rank, self.world)
+        if tracker_factory is None:
+            def tracker_factory(n_local, **kw):
+                return StreamTracker(width, height, n_streams=n_local, **kw)
+        self.local = tracker_factory(len(self.streams), **tracker_kw) if self.streams else None
+        self.last = None
+
+    def select(self, per_stream):
+        """this rank's rows of a per-stream array / list indexed by global stream id"""
+        return [per_stream[s] for s in self.streams]
+
+    def step(self, frames_local, imu_local, **kw):
+        """frames_local / imu_local: this rank's streams in the order of `self.streams` (see `select`)."""
+        if self.local is None:
+            self.last = None
+            return None
+        out = self.local.step(frames_local, imu_local, **kw)
+        self.last = out[0] if isinstance(out, tuple) else out
+        return out
+
+    def gather_velocities(self):
+        """(n_streams, 3) velocities of the last step on every rank; rows of streams that did not solve are NaN."""
+        from .simulation import gather_stream_velocities
+        import torch.distributed as dist
+        v = np.zeros((len(self.streams), 3))
+        if self.last is not None:
+            v = np.where((self.last["flags"] & _lib.TRACK_SOLVED)[:, None] != 0, self.last["v"], np.nan)
+        if self.world == 1:
+            table = np.full((self.n_streams, 3), np.nan)
+            table[self.streams] = v
+            return table
+        dev = None
+        if dist.get_backend(self.group) == "nccl":
+            import torch
+            dev = torch.device("cuda", self.local.ctx.device if self.local is not None else 0)
+        # NaN rows cannot ride a sum: send a validity column alongside
+        ok = ~np.isnan(v[:, 0])
+        vv = np.where(ok[:, None], v, 0.0)
+        table = gather_stream_velocities(vv, self.streams, self.n_streams, self.group, dev)
+        valid = gather_stream_velocities(np.repeat(ok[:, None].astype(float), 3, axis=1), self.streams, self.n_streams,
+                                         self.group, dev)
+        table[valid[:, 0] == 0] = np.nan
+        return table
+
+    def close(self):
+        if self.local is not None:
+            self.local.close()
+            self.local = None

@@ -168,3 +168,77 @@ def test_overlap_merge_and_stream_gather_world_size_2_gloo():
         assert lo == min(d1.min(), d2.min()) and hi == max(d1.max(), d2.max())
         assert ov == expect
         assert np.array_equal(np.array(v), np.array([[i, 2.0 * i, -i] for i in range(7)], dtype=float))
+
+
+class _FakeTracker:
+    """stands in for StreamTracker (which needs a GPU): stream i reports v = (global id, step, -1); odd ids do not solve"""
+
+    def __init__(self, ids):
+        self.ids, self.k = ids, 0
+
+    def step(self, frames, imu):
+        from ofb200 import _lib
+        self.k += 1
+        r = np.zeros(len(self.ids), _lib.TRACK_RESULT_DTYPE)
+        for j, g in enumerate(self.ids):
+            r["v"][j] = [g, self.k, -1.0]
+            r["flags"][j] = 0 if g % 2 else 1
+        return r
+
+    def close(self):
+        pass
+
+
+def _fleet_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import ofb200
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    made = {}
+
+    def factory(n_local, **kw):
+        made["n"] = n_local
+        return _FakeTracker(ofb200.simulation.stream_shard(9, rank, world))
+    fleet = ofb200.FleetTracker(9, 64, 48, tracker_factory=factory)
+    assert made["n"] == len(fleet.streams) and fleet.select(list(range(100, 109))) == [100 + s for s in fleet.streams]
+    fleet.step(None, None)
+    fleet.step(None, None)
+    q.put((rank, fleet.streams, fleet.gather_velocities().tolist()))
+    fleet.close()
+    dist.destroy_process_group()
+
+
+def test_fleet_tracker_shards_and_gathers_world_size_2_gloo():
+    """FleetTracker: streams s mod world per rank, one all-reduce merges the last step's velocities; streams that did
+    not solve come back as NaN rows on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fleet_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert outs[0][1] == [0, 2, 4, 6, 8] and outs[1][1] == [1, 3, 5, 7]
+    for _, _, table in outs:
+        t = np.array(table)
+        assert t.shape == (9, 3)
+        for g in range(9):
+            if g % 2:
+                assert np.isnan(t[g]).all()
+            else:
+                assert t[g].tolist() == [g, 2.0, -1.0]
+
+
+def test_fleet_tracker_single_process():
+    import ofb200
+    fleet = ofb200.FleetTracker(4, 64, 48, tracker_factory=lambda n, **kw: _FakeTracker([0, 1, 2, 3]))
+    assert fleet.streams == [0, 1, 2, 3] and fleet.world == 1
+    fleet.step(None, None)
+    t = fleet.gather_velocities()
+    assert t[0].tolist() == [0.0, 1.0, -1.0] and np.isnan(t[1]).all() and t[2].tolist() == [2.0, 1.0, -1.0]
+    fleet.close()
