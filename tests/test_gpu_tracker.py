@@ -407,3 +407,26 @@ def test_odd_geometry_matches_the_pair_path(ofb200, ctx, bgr):
         assert trk.graph_steps() >= 2
     finally:
         trk.close()
+
+
+def test_fleet_tracker_single_rank_equals_stream_tracker(ofb200, ctx):
+    """ofb200.FleetTracker without a process group (world size 1): the gathered velocity table is the StreamTracker's
+    (the multi-rank gather is covered by the gloo test in test_host_logic.py and by tools/fleet_smoke.py over NCCL)."""
+    frames, imus, kw = tc.build("module")
+    S, T = len(frames), 3
+    fleet = ofb200.FleetTracker(S, tc.W, tc.H, ctx=ctx, **kw)
+    ref = make_gpu_tracker(ofb200, ctx, kw, S)
+    try:
+        assert fleet.streams == list(range(S)) and fleet.world == 1
+        for k in range(T):
+            samples = [imus[s][k] for s in range(S)]
+            fr = np.stack([frames[s][k] for s in range(S)])
+            fleet.step(np.stack(fleet.select(list(fr))), imu_records(ofb200, samples), v_prior=priors(samples))
+            r = ref.step(fr, imu_records(ofb200, samples), v_prior=priors(samples))
+        table = fleet.gather_velocities()
+        solved = (r["flags"] & 1) != 0
+        assert np.array_equal(np.isnan(table[:, 0]), ~solved)
+        assert np.array_equal(table[solved], r["v"][solved])
+    finally:
+        fleet.close()
+        ref.close()
