@@ -10,8 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libofb200.so")
 
 OFB_OK, OFB_E_INVALID, OFB_E_CUDA, OFB_E_NOMEM, OFB_E_UNSUPPORTED = 0, -1, -2, -3, -4
-VARIANT_NODE, VARIANT_EXP, VARIANT_SIM = 0, 1, 2
+VARIANT_NODE, VARIANT_EXP, VARIANT_SIM, VARIANT_MODULE = 0, 1, 2, 3
 VARIANTS = {"node": VARIANT_NODE, "exp": VARIANT_EXP, "sim": VARIANT_SIM}
+TRACKER_VARIANTS = dict(VARIANTS, module=VARIANT_MODULE)
 LK_USE_INITIAL_FLOW = 4
 MC_MAX_POINTS = 256
 
@@ -35,14 +36,14 @@ class ImuSample(C.Structure):
 
 class PairResult(C.Structure):
     _fields_ = [("v", C.c_double * 3), ("s", C.c_double * 3), ("res", C.c_double), ("rank", C.c_int),
-                ("n_features", C.c_int), ("n_tracked", C.c_int)]
+                ("n_features", C.c_int), ("n_tracked", C.c_int), ("flags", C.c_int)]
 
 
 class TrackerCfg(C.Structure):
     _fields_ = [("pair", PairCfg), ("n_streams", C.c_int), ("min_features", C.c_int), ("topup_mode", C.c_int),
                 ("mask_radius", C.c_int), ("bgr_input", C.c_int), ("max_speed", C.c_double),
                 ("dummy_value", C.c_double), ("gate_mode", C.c_int), ("gate_T", C.c_double), ("min_solve", C.c_int),
-                ("borrow_frames", C.c_int)]
+                ("borrow_frames", C.c_int), ("v_init", C.c_double * 3)]
 
 
 class TrackResult(C.Structure):
@@ -66,7 +67,7 @@ class McSums(C.Structure):
 
 IMU_DTYPE = np.dtype([("d", "<f8"), ("n", "<f8", 3), ("w", "<f8", 3), ("t", "<f8", 3)])
 RESULT_DTYPE = np.dtype([("v", "<f8", 3), ("s", "<f8", 3), ("res", "<f8"), ("rank", "<i4"),
-                         ("n_features", "<i4"), ("n_tracked", "<i4")], align=True)
+                         ("n_features", "<i4"), ("n_tracked", "<i4"), ("flags", "<i4")], align=True)
 TRACK_RESULT_DTYPE = np.dtype([("v", "<f8", 3), ("s", "<f8", 3), ("res", "<f8"), ("rank", "<i4"), ("flags", "<i4"),
                                ("n_prev", "<i4"), ("n_tracked", "<i4"), ("n_kept", "<i4"), ("n_added", "<i4"),
                                ("n_points", "<i4")], align=True)
@@ -74,6 +75,7 @@ TOPUP_APPEND_MASKED, TOPUP_APPEND, TOPUP_REPLACE = 0, 1, 2
 TOPUP_MODES = {"node": TOPUP_APPEND_MASKED, "exp": TOPUP_APPEND, "module": TOPUP_REPLACE}
 GATE_NONE, GATE_R_GE, GATE_R_LE = 0, 1, 2
 TRACK_SOLVED, TRACK_OVERFLOW = 1, 2
+PAIR_OVERFLOW = 2
 MCSUMS_DTYPE = np.dtype([("n", "<f8"), ("sum_dv", "<f8", 3), ("sum_dv2", "<f8", 3), ("sum_R", "<f8")])
 
 _lib = None
@@ -110,6 +112,8 @@ _SIGNATURES = {
     "ofb_pyrlk": (i32, [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, f64, i32, f64, vp, vp, vp]),
     "ofb_solve_velocity": (i32, [vp, i32, vp, vp, i32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "ofb_solve_velocity_batched": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ofb_solve_velocity_module": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "ofb_advect_points": (i32, [vp, vp, i32, vp, vp, f64, vp, vp, i32, vp, vp, vp]),
     "ofb_generate_flow": (i32, [vp, vp, i32, vp, vp, f64, vp, vp, vp]),
     "ofb_r_tilde": (i32, [vp, vp, vp, i32, i32, vp, vp, f64, vp, vp]),
     "ofb_feasibility": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp]),

@@ -70,7 +70,7 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { OFB_NSCRATCH = 25, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6 };
+enum { OFB_NSCRATCH = 25, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6, OFB_NFUNC_SLOTS = 32 };
 
 struct ofb_ctx {
     int device = 0;
@@ -78,6 +78,9 @@ struct ofb_ctx {
     bool own_stream = false;
     int sm_count = 148;
     uint64_t launches = 0;
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: what this context has already
+    // requested for each kernel that needs more than 48 KB (slot = FS_* below). Per context, hence per device.
+    size_t func_smem[OFB_NFUNC_SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf scratch[OFB_NSCRATCH];   // role-indexed scratch arenas (see each stage)
     PinBuf pin[4];
@@ -179,6 +182,25 @@ static inline int ofb_finish_out(ofb_ctx* ctx, OutStage* outs, int n)
     do { (ctx)->launches++; OFB_CUDA(cudaGetLastError()); } while (0)
 
 static inline int ofb_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// kernels launched with more than 48 KB of dynamic shared memory (slots of ofb_ctx::func_smem)
+enum {
+    FS_MARCH = 0,            // + 2 * {bs 3, 7, 12} + write_map          (6 slots)
+    FS_TILE = 6,             // + 2 * {bs 3, 7, runtime} + write_map     (6 slots)
+    FS_CAND = 12,            // + write_map                              (2 slots)
+    FS_SELECT = 14,          // + {256, 512, 1024 threads}               (3 slots)
+    FS_LK = 17,
+    FS_PYR_TOP = 18
+};
+// Raises a kernel's dynamic shared-memory limit on the context's device when this context has not done so yet.
+template <class F>
+static inline int ofb_ensure_smem(ofb_ctx* ctx, int slot, F func, size_t smem)
+{
+    if (smem <= 48 * 1024 || smem <= ctx->func_smem[slot]) return OFB_OK;
+    OFB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->func_smem[slot] = smem;
+    return OFB_OK;
+}
 
 // stage entry points implemented in the per-stage translation units (device pointers only)
 int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* pyr);

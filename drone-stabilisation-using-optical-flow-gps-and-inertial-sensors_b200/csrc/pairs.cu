@@ -32,10 +32,12 @@ struct TrackLoader {
         ux = (double)dx * fs; uy = (double)dy * fs;                // node:235
         return true;
     }
+    __device__ bool dist(int, int, double&) const { return false; }
 };
 
 __global__ void __launch_bounds__(OFB_SOLVE_THREADS)
-pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict__ imu, ofb_pair_result* __restrict__ out)
+pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict__ imu, ofb_pair_result* __restrict__ out,
+                  const FeatImageState* __restrict__ det)
 {
     int f = blockIdx.x;
     const ofb_imu_sample& s = imu[f];
@@ -46,6 +48,7 @@ pair_solve_kernel(TrackLoader ld, int variant, const ofb_imu_sample* __restrict_
         r.res = o.res; r.rank = o.rank;
         r.n_features = ld.end(f);
         r.n_tracked = o.count;
+        r.flags = (det && det[f].overflow) ? OFB_PAIR_OVERFLOW : 0;     // detector ran out of candidate slots
         out[f] = r;
     }
 }
@@ -82,8 +85,8 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
     float* cn = d_next + (size_t)c0 * 2 * K;
     uint8_t* cs = d_stat + (size_t)c0 * K;
     const int* counts; int counts_stride;
+    FeatImageState* st = nullptr;
     if (cfg->detect) {
-        FeatImageState* st = nullptr;
         unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
         ctx->fork_after_eig = overlap;
         int fr = ofb_features_device(ctx, pp->level0, w, h, pp->level0_pitch, pp->level0_stride, n, nullptr, 0, 0, K,
@@ -118,7 +121,7 @@ static int run_pairs_chunk(ofb_ctx* ctx, const ofb_pair_cfg* cfg, ofb_pyr* pp, o
                           cfg->max_level, cfg->max_count, cfg->eps, 0, cfg->min_eig_thr, cn, cs, ctx->scratch[SC_ERR].as<float>()));
     STAGE_MARK(4);
     TrackLoader ld{cp, cn, cs, counts, counts_stride, (size_t)K, cfg->cx, cfg->cy, cfg->pos_scale, cfg->flow_scale};
-    pair_solve_kernel<<<n, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, dimu + c0, d_res + c0);
+    pair_solve_kernel<<<n, OFB_SOLVE_THREADS, 0, ctx->stream>>>(ld, cfg->variant, dimu + c0, d_res + c0, st);
     OFB_LAUNCH_CHECK(ctx);
     STAGE_MARK(5);
 #undef STAGE_MARK

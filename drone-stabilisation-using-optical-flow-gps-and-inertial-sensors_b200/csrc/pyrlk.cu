@@ -549,11 +549,7 @@ int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_s
     }
     size_t wsm = ofb_lk_warp_smem(win_w, win_h);
     size_t smem = wsm * LK_WARPS;
-    static size_t lk_smem_set = 0;
-    if (smem > 48 * 1024 && smem > lk_smem_set) {
-        OFB_CUDA(cudaFuncSetAttribute(lk_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lk_smem_set = smem;
-    }
+    OFB_TRY(ofb_ensure_smem(ctx, FS_LK, lk_track_kernel, smem));
     if (n_uniform <= 0) return OFB_OK;
     dim3 grid(ofb_div_up(n_uniform, LK_WARPS), n_pairs);
     lk_track_kernel<<<grid, LK_WARPS * 32, smem, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts, counts_stride,

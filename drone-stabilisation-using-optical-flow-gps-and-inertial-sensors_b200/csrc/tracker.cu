@@ -79,6 +79,7 @@ struct KeptLoader {
         ux = (double)dx * fs; uy = (double)dy * fs;                  // node:235
         return true;
     }
+    __device__ bool dist(int, int, double&) const { return false; }   // MODULE: distances from the prior velocity
 };
 
 // of.r_tilde (of_library.py:365-386, 5-argument form), feasibility value only
@@ -110,6 +111,9 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         const double* src = v_prior ? v_prior + 3 * s : T.vlast + 3 * s;
         vp[0] = src[0]; vp[1] = src[1]; vp[2] = src[2];
     }
+    // r_tilde is 1 for every point when the prior velocity is zero (of_library.py:377-379): a "keep r <= T" gate
+    // would then drop every point and the stream could never solve its first velocity -- no prior, no gate
+    const bool have_prior = vp[0] != 0.0 || vp[1] != 0.0 || vp[2] != 0.0;
     const double n3[3] = {im.n[0], im.n[1], im.n[2]};
     // static_immobile compares float32 arrays with a Python scalar: the threshold takes the arrays' type
     const float speed_thr = T.max_speed > 0 ? (float)(T.max_speed / im.d) : 0.f;
@@ -131,7 +135,7 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
                 const bool not_dummy = px != dummy && py != dummy;
                 keep = speed_ok && not_dummy;
             }
-            if (keep && T.have_prev && T.gate_mode != OFB_GATE_NONE) {              // node:238-245, of_module.py:125-131
+            if (keep && T.have_prev && T.gate_mode != OFB_GATE_NONE && have_prior) { // node:238-245, of_module.py:125-131
                 const float dx = qx - px, dy = qy - py;
                 const double r = r_tilde_point(((double)qx - T.cx) * T.ps, ((double)qy - T.cy) * T.ps, (double)dx * T.fs,
                                                (double)dy * T.fs, n3, vp);
@@ -165,7 +169,7 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
     const bool solve = T.have_prev && kept >= T.min_solve && kept > 0;
     if (solve) {
         KeptLoader ld{T.kept_prev, T.kept_next, kept, (size_t)T.cap, T.cx, T.cy, T.ps, T.fs};
-        o = ofb_block_solve(ld, s, T.variant, im.d, im.n, im.w, im.t);
+        o = ofb_block_solve(ld, s, T.variant, im.d, im.n, im.w, im.t, vp);    // vp: MODULE's per-point distances (of_module.py:125)
     }
     // the detector's per-image state and (for streams that will top up) its min-distance cell grid start clean
     if (kept <= T.min_features)
@@ -305,6 +309,17 @@ int render_mask_device(ofb_ctx* ctx, uint8_t* mask, int w, int h, int mpitch, si
 
 }  // namespace
 
+// every stream's prior velocity (the r_tilde gate's `self.vel`) starts from cfg.v_init
+static cudaError_t tracker_seed_prior(ofb_tracker* t)
+{
+    const int S = t->cfg.n_streams;
+    std::vector<double> v((size_t)3 * S);
+    for (int s = 0; s < S; ++s) for (int k = 0; k < 3; ++k) v[3 * s + k] = t->cfg.v_init[k];
+    cudaError_t e = cudaMemcpyAsync(t->vlast.p, v.data(), sizeof(double) * 3 * S, cudaMemcpyHostToDevice, t->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t->ctx->stream);          // v is a local
+    return e;
+}
+
 extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_tracker** out)
 {
     OFB_REQUIRE(ctx && cfg && out, "tracker_create: null argument");
@@ -312,7 +327,7 @@ extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_
     OFB_REQUIRE(p.width >= 2 && p.height >= 2, "tracker_create: bad image geometry");
     OFB_REQUIRE(p.max_corners > 0, "tracker_create: max_features (pair.max_corners) must be positive");
     OFB_REQUIRE(p.max_level >= 0, "tracker_create: max_level must be >= 0");
-    OFB_REQUIRE(p.variant >= 0 && p.variant <= 2, "tracker_create: unknown variant");
+    OFB_REQUIRE(p.variant >= 0 && p.variant <= OFB_VARIANT_MODULE, "tracker_create: unknown variant");
     OFB_REQUIRE(cfg->n_streams >= 1 && cfg->n_streams <= 65535, "tracker_create: n_streams must be in 1..65535");
     OFB_REQUIRE(cfg->min_features >= 0 && cfg->min_features < p.max_corners,
                 "tracker_create: min_features must be in 0..max_features-1");
@@ -349,7 +364,7 @@ extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);      // hw is a local
     }
     if (ce == cudaSuccess) ce = cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * S, ctx->stream);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * S, ctx->stream);
+    if (ce == cudaSuccess) ce = tracker_seed_prior(t);
     if (ce != cudaSuccess) {
         ofb_set_error("tracker_create: %s", cudaGetErrorString(ce));
         ofb_tracker_destroy(t);
@@ -383,7 +398,7 @@ extern "C" int ofb_tracker_reset(ofb_tracker* t)
     OFB_CUDA(cudaSetDevice(t->ctx->device));
     t->have_prev = false;
     OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * t->cfg.n_streams, t->ctx->stream));
-    OFB_CUDA(cudaMemsetAsync(t->vlast.p, 0, sizeof(double) * 3 * t->cfg.n_streams, t->ctx->stream));
+    OFB_CUDA(tracker_seed_prior(t));
     return OFB_OK;
 }
 

@@ -17,14 +17,16 @@
 
 namespace {
 
-struct PointsF64 {          // x,u as n x 2 doubles, frame f covers [offsets[f], offsets[f+1])
+struct PointsF64 {          // x,u as n x ld doubles, frame f covers [offsets[f], offsets[f+1])
     const double* x; const double* u; const int* offsets; int single_n;
+    int ld = 2; const double* dists = nullptr;        // MODULE variant: optional per-point distances
     __device__ int begin(int f) const { return offsets ? offsets[f] : 0; }
     __device__ int end(int f) const { return offsets ? offsets[f + 1] : single_n; }
     __device__ bool load(int, int i, double& px, double& py, double& ux, double& uy) const {
-        px = x[2 * i]; py = x[2 * i + 1]; ux = u[2 * i]; uy = u[2 * i + 1];
+        px = x[ld * i]; py = x[ld * i + 1]; ux = u[ld * i]; uy = u[ld * i + 1];
         return true;
     }
+    __device__ bool dist(int, int i, double& d) const { if (!dists) return false; d = dists[i]; return true; }
 };
 
 template <class Loader>
@@ -32,14 +34,14 @@ __global__ void __launch_bounds__(OFB_SOLVE_THREADS)
 solve_velocity_kernel(Loader ld, int variant, const double* __restrict__ d_arr, const double* __restrict__ n_arr,
                       const double* __restrict__ w_arr, const double* __restrict__ t_arr, int d_stride, int imu_stride,
                       double* __restrict__ v_out, double* __restrict__ res_out, int* __restrict__ rank_out,
-                      double* __restrict__ s_out, int* __restrict__ count_out)
+                      double* __restrict__ s_out, int* __restrict__ count_out, const double* __restrict__ vprior_arr)
 {
     int f = blockIdx.x;
     const double* n3 = n_arr + (size_t)f * imu_stride;
     const double* w3 = w_arr + (size_t)f * imu_stride;
     const double* t3 = t_arr ? t_arr + (size_t)f * imu_stride : nullptr;
-    double d = d_arr[(size_t)f * d_stride];
-    OfbSolveOut o = ofb_block_solve(ld, f, variant, d, n3, w3, t3);
+    double d = d_arr ? d_arr[(size_t)f * d_stride] : 1.0;
+    OfbSolveOut o = ofb_block_solve(ld, f, variant, d, n3, w3, t3, vprior_arr ? vprior_arr + (size_t)f * imu_stride : nullptr);
     if (threadIdx.x == 0) {
         v_out[3 * f] = o.v[0]; v_out[3 * f + 1] = o.v[1]; v_out[3 * f + 2] = o.v[2];
         if (res_out) res_out[f] = o.res;
@@ -61,6 +63,33 @@ __global__ void generate_flow_kernel(const double* __restrict__ x, int n, double
     double s = nx / d;
     u[2 * i]     = s * (v.x - v.z * px) + (cx - cz * px);
     u[2 * i + 1] = s * (v.y - v.z * py) + (cy - cz * py);
+}
+
+// Time-evolution sweep (simulation.py:472-501): between two steps every point moves by its own translational flow,
+// data += generate_test_data(data, v, 0, h, n, t), and the height grows by v.n. A point's trajectory depends on no other
+// point, so one thread walks all k steps of its point (one launch instead of k dependent host round trips) and
+// writes, per step, the position and the true flow of the step (generate_test_data with the real gyro rate).
+__global__ void advect_points_kernel(const double* __restrict__ x0, int n, double3 v, double3 vlev, double3 w, double d0,
+                                     double dstep, double3 nrm, int k, double* __restrict__ pos_out,
+                                     double* __restrict__ flow_out, double* __restrict__ d_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double px = x0[2 * i], py = x0[2 * i + 1], d = d0;
+    for (int s = 0; s < k; ++s) {
+        const size_t o = 2 * ((size_t)s * n + i);
+        pos_out[o] = px; pos_out[o + 1] = py;
+        const double nx = nrm.x * px + nrm.y * py + nrm.z, sc = nx / d;
+        if (flow_out) {     // simulation.py:7-12 with v' = v + w x t
+            const double cx = w.y - w.z * py, cy = w.z * px - w.x, cz = w.x * py - w.y * px;
+            flow_out[o] = sc * (vlev.x - vlev.z * px) + (cx - cz * px);
+            flow_out[o + 1] = sc * (vlev.y - vlev.z * py) + (cy - cz * py);
+        }
+        if (d_out && i == 0) d_out[s] = d;
+        const double ax = sc * (v.x - v.z * px), ay = sc * (v.y - v.z * py);     // gyro rate 0: v' = v (simulation.py:497)
+        px += ax; py += ay;
+        d += dstep;                                                              // simulation.py:499
+    }
 }
 
 __global__ void r_tilde_kernel(const double* __restrict__ x, const double* __restrict__ u, int n, int ld,
@@ -126,8 +155,11 @@ extern "C" int ofb_solve_velocity_batched(ofb_ctx* ctx, int variant, const doubl
         OFB_CUDA(cudaMemcpyAsync(hoff.data(), offsets, sizeof(int) * (n_frames + 1), cudaMemcpyDeviceToHost, ctx->stream));
         OFB_CUDA(cudaStreamSynchronize(ctx->stream));
     } else memcpy(hoff.data(), offsets, sizeof(int) * (n_frames + 1));
-    int total = hoff[n_frames];
-    OFB_REQUIRE(total >= 0, "solve_velocity_batched: bad offsets");
+    OFB_REQUIRE(hoff[0] >= 0, "solve_velocity_batched: offsets[0] = %d is negative", hoff[0]);
+    for (int f = 0; f < n_frames; ++f)
+        OFB_REQUIRE(hoff[f + 1] >= hoff[f], "solve_velocity_batched: offsets must be non-decreasing (offsets[%d] = %d > offsets[%d] = %d)",
+                    f, hoff[f], f + 1, hoff[f + 1]);
+    int total = hoff[n_frames];                       // x and u must hold at least this many rows
     const void *dx, *du, *doff, *dd, *dn, *dw, *dt = nullptr;
     OFB_TRY(ofb_stage_in(ctx, SC_IN0, x, sizeof(double) * 2 * (size_t)total, &dx));
     OFB_TRY(ofb_stage_in(ctx, SC_IN1, u, sizeof(double) * 2 * (size_t)total, &du));
@@ -145,7 +177,41 @@ extern "C" int ofb_solve_velocity_batched(ofb_ctx* ctx, int variant, const doubl
     if (total == 0 && !dx) { ld.x = ld.u = nullptr; }
     solve_velocity_kernel<PointsF64><<<n_frames, OFB_SOLVE_THREADS, 0, ctx->stream>>>(
         ld, variant, (const double*)dd, (const double*)dn, (const double*)dw, (const double*)dt, 1, 3,
-        (double*)o[0].dev, (double*)o[1].dev, (int*)o[2].dev, (double*)o[3].dev, nullptr);
+        (double*)o[0].dev, (double*)o[1].dev, (int*)o[2].dev, (double*)o[3].dev, nullptr, nullptr);
+    OFB_LAUNCH_CHECK(ctx);
+    return ofb_finish_out(ctx, o, 4);
+}
+
+extern "C" int ofb_solve_velocity_module(ofb_ctx* ctx, const double* x, const double* u, int n, int ld, const double* dist,
+                                         const double n3[3], const double* v_prior,
+                                         double v_out[3], double* res, int* rank, double s_out[3])
+{
+    OFB_REQUIRE(ctx && n3 && v_out, "solve_velocity_module: null argument");
+    OFB_REQUIRE(ld == 2 || ld == 3, "solve_velocity_module: leading dimension must be 2 or 3");
+    OFB_REQUIRE(n >= 0, "solve_velocity_module: negative point count");
+    OFB_REQUIRE(n == 0 || (x && u), "solve_velocity_module: null points");
+    OFB_REQUIRE(dist || v_prior, "solve_velocity_module: needs per-point distances or the prior velocity they derive from");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const double zero3[3] = {0.0, 0.0, 0.0};
+    const void *dx = nullptr, *du = nullptr, *dd = nullptr, *dn, *dw, *dvp = nullptr;
+    if (n) {
+        OFB_TRY(ofb_stage_in(ctx, SC_IN0, x, sizeof(double) * ld * (size_t)n, &dx));
+        OFB_TRY(ofb_stage_in(ctx, SC_IN1, u, sizeof(double) * ld * (size_t)n, &du));
+        if (dist) OFB_TRY(ofb_stage_in(ctx, SC_IN2, dist, sizeof(double) * (size_t)n, &dd));
+    }
+    OFB_TRY(ofb_stage_in(ctx, SC_IN4, n3, sizeof(double) * 3, &dn));
+    OFB_TRY(ofb_stage_in(ctx, SC_IN5, zero3, sizeof(double) * 3, &dw));       // (pageable source: the copy is staged at once)
+    if (v_prior) OFB_TRY(ofb_stage_in(ctx, SC_TMP0, v_prior, sizeof(double) * 3, &dvp));
+    OutStage o[4];
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT0, v_out, sizeof(double) * 3, &o[0]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT1, res, sizeof(double), &o[1]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT2, rank, sizeof(int), &o[2]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT3, s_out, sizeof(double) * 3, &o[3]));
+    PointsF64 ldr{(const double*)dx, (const double*)du, nullptr, n};
+    ldr.ld = ld; ldr.dists = (const double*)dd;
+    solve_velocity_kernel<PointsF64><<<1, OFB_SOLVE_THREADS, 0, ctx->stream>>>(
+        ldr, OFB_VARIANT_MODULE, nullptr, (const double*)dn, (const double*)dw, nullptr, 1, 3,
+        (double*)o[0].dev, (double*)o[1].dev, (int*)o[2].dev, (double*)o[3].dev, nullptr, (const double*)dvp);
     OFB_LAUNCH_CHECK(ctx);
     return ofb_finish_out(ctx, o, 4);
 }
@@ -184,6 +250,30 @@ extern "C" int ofb_generate_flow(ofb_ctx* ctx, const double* x, int n, const dou
     generate_flow_kernel<<<ofb_div_up(n, 256), 256, 0, ctx->stream>>>((const double*)dx, n, v, w, d, d3(n3), (double*)o.dev);
     OFB_LAUNCH_CHECK(ctx);
     return ofb_finish_out(ctx, &o, 1);
+}
+
+extern "C" int ofb_advect_points(ofb_ctx* ctx, const double* x0, int n, const double v3[3], const double w3[3], double d0,
+                                 const double n3[3], const double t3[3], int k, double* pos_out, double* flow_out,
+                                 double* d_out)
+{
+    OFB_REQUIRE(ctx && v3 && w3 && n3 && pos_out, "advect_points: null argument");
+    OFB_REQUIRE(n >= 0 && k >= 1, "advect_points: bad point or step count");
+    if (n == 0) return OFB_OK;
+    OFB_REQUIRE(x0, "advect_points: null points");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const void* dx;
+    OFB_TRY(ofb_stage_in(ctx, SC_IN0, x0, sizeof(double) * 2 * (size_t)n, &dx));
+    OutStage o[3];
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT0, pos_out, sizeof(double) * 2 * (size_t)n * k, &o[0]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT1, flow_out, sizeof(double) * 2 * (size_t)n * k, &o[1]));
+    OFB_TRY(ofb_stage_out(ctx, SC_OUT2, d_out, sizeof(double) * (size_t)k, &o[2]));
+    double3 v = d3(v3), w = d3(w3), vl = v;
+    if (t3) { vl.x += w.y * t3[2] - w.z * t3[1]; vl.y += w.z * t3[0] - w.x * t3[2]; vl.z += w.x * t3[1] - w.y * t3[0]; }
+    const double dstep = v3[0] * n3[0] + v3[1] * n3[1] + v3[2] * n3[2];
+    advect_points_kernel<<<ofb_div_up(n, 128), 128, 0, ctx->stream>>>((const double*)dx, n, v, vl, w, d0, dstep, d3(n3), k,
+                                                                      (double*)o[0].dev, (double*)o[1].dev, (double*)o[2].dev);
+    OFB_LAUNCH_CHECK(ctx);
+    return ofb_finish_out(ctx, o, 3);
 }
 
 extern "C" int ofb_r_tilde(ofb_ctx* ctx, const double* x, const double* u, int n, int ld, const double n3[3],

@@ -10,10 +10,12 @@ struct OfbSolveOut { double v[3]; double s[3]; double res; int rank; int count; 
 // Per-point contribution. X=(px,py,1), beta = X x (u3 + X x w).
 //   SIM  : A_i = (n.X)[X]x, b_i = beta            simulation.py:19-23
 //   NODE/EXP: A_i = [X]x,   b_i = beta/(n.X)      node:34-38, evaluate_exp.py:22-26
+//   MODULE: A_i = [X]x / dist_i, b_i = A_i u3 / (n.X) = [X]x u3 / (dist_i (n.X)); no gyro term (the caller passes
+//           w = 0), right-hand side not scaled by a common height    optical_flow_experiments/of_module.py:141-146
 struct OfbPointTerms { double wA, wb, bx, by, bz; };
 
 __device__ __forceinline__ OfbPointTerms ofb_point_terms(int variant, double px, double py, double ux, double uy,
-                                                         const double n3[3], const double w3[3])
+                                                         const double n3[3], const double w3[3], double inv_dist = 1.0)
 {
     // a = X x w
     double ax = py * w3[2] - w3[1], ay = w3[0] - px * w3[2], az = px * w3[1] - py * w3[0];
@@ -22,8 +24,20 @@ __device__ __forceinline__ OfbPointTerms ofb_point_terms(int variant, double px,
     t.bx = py * cz - cy; t.by = cx - px * cz; t.bz = px * cy - py * cx;
     double nx = n3[0] * px + n3[1] * py + n3[2];
     if (variant == OFB_VARIANT_SIM) { t.wA = nx; t.wb = 1.0; }
+    else if (variant == OFB_VARIANT_MODULE) { t.wA = inv_dist; t.wb = inv_dist / nx; }
     else { t.wA = 1.0; t.wb = 1.0 / nx; }
     return t;
+}
+
+// 1 / dist_i of the older 4-argument of.r_tilde (sensor_precision_experiments/pixhawk_pure_IMU/of_library.py:365-384,
+// called at of_module.py:125): dist_i = (n.X) |X x v| / |X x u3|
+__device__ __forceinline__ double ofb_module_inv_dist(double px, double py, double ux, double uy, const double n3[3],
+                                                      const double v[3])
+{
+    const double a0 = py * v[2] - v[1], a1 = v[0] - px * v[2], a2 = px * v[1] - py * v[0];      // X x v
+    const double b0 = -uy, b1 = ux, b2 = px * uy - py * ux;                                     // X x u3
+    const double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2), nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
+    return nb / ((n3[0] * px + n3[1] * py + n3[2]) * na);
 }
 
 __device__ __forceinline__ double ofb_warp_sum(double v)
@@ -52,21 +66,38 @@ __device__ __forceinline__ void ofb_block_sum(double (&acc)[K], double* smem /* 
     }
 }
 
-// Loader concept: begin(f), end(f), load(f, i, px, py, ux, uy) -> bool (false = point skipped).
+// Loader concept: begin(f), end(f), load(f, i, px, py, ux, uy) -> bool (false = point skipped),
+// dist(f, i, d) -> bool (MODULE variant: true = per-point distance supplied by the caller, false = derive it from the
+// prior velocity `vprior` with the 4-argument r_tilde).
 template <class Loader>
 __device__ OfbSolveOut ofb_block_solve(const Loader& ld, int f, int variant, double d, const double* n3g,
-                                       const double* w3g, const double* t3g)
+                                       const double* w3g, const double* t3g, const double* vprior = nullptr)
 {
     __shared__ double red[11 * 32];
+    const bool module = variant == OFB_VARIANT_MODULE;
     double n3[3] = {n3g[0], n3g[1], n3g[2]};
     double w3[3] = {w3g[0], w3g[1], w3g[2]};
+    double vp[3] = {0.0, 0.0, 0.0};
+    if (module) {                                   // flow is used as given (no gyro term), rhs is not scaled by a height
+        w3[0] = w3[1] = w3[2] = 0.0; d = 1.0;
+        if (vprior) { vp[0] = vprior[0]; vp[1] = vprior[1]; vp[2] = vprior[2]; }
+    }
+    // a zero prior would make every derived distance zero (the reference then divides by zero): unit distances instead
+    const bool unit_dist = module && vp[0] == 0.0 && vp[1] == 0.0 && vp[2] == 0.0;
+    auto inv_dist = [&](int i, double px, double py, double ux, double uy) -> double {
+        if (!module) return 1.0;
+        double di;
+        if (ld.dist(f, i, di)) return 1.0 / di;
+        if (unit_dist) return 1.0;
+        return ofb_module_inv_dist(px, py, ux, uy, n3, vp);
+    };
     int i0 = ld.begin(f), i1 = ld.end(f);
     // M (6), g (3), count
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double px, py, ux, uy;
         if (!ld.load(f, i, px, py, ux, uy)) continue;
-        OfbPointTerms t = ofb_point_terms(variant, px, py, ux, uy, n3, w3);
+        OfbPointTerms t = ofb_point_terms(variant, px, py, ux, uy, n3, w3, inv_dist(i, px, py, ux, uy));
         double w2 = t.wA * t.wA;
         double xx = px * px, yy = py * py;
         // |X|^2 I - X X^T
@@ -112,7 +143,7 @@ __device__ OfbSolveOut ofb_block_solve(const Loader& ld, int f, int variant, dou
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         double px, py, ux, uy;
         if (!ld.load(f, i, px, py, ux, uy)) continue;
-        OfbPointTerms t = ofb_point_terms(variant, px, py, ux, uy, n3, w3);
+        OfbPointTerms t = ofb_point_terms(variant, px, py, ux, uy, n3, w3, inv_dist(i, px, py, ux, uy));
         double rx = t.wA * (py * v[2] - v[1]) - d * t.wb * t.bx;
         double ry = t.wA * (v[0] - px * v[2]) - d * t.wb * t.by;
         double rz = t.wA * (px * v[1] - py * v[0]) - d * t.wb * t.bz;
@@ -121,7 +152,7 @@ __device__ OfbSolveOut ofb_block_solve(const Loader& ld, int f, int variant, dou
     ofb_block_sum<1>(r, red);
     o.res = r[0];
     // lever arm: v_obs = v' - w x t   (simulation.py:28, evaluate_exp.py:29); NODE has none
-    if (variant != OFB_VARIANT_NODE && t3g) {
+    if (variant != OFB_VARIANT_NODE && !module && t3g) {
         v[0] -= w3[1] * t3g[2] - w3[2] * t3g[1];
         v[1] -= w3[2] * t3g[0] - w3[0] * t3g[2];
         v[2] -= w3[0] * t3g[1] - w3[1] * t3g[0];

@@ -236,10 +236,10 @@ def _to_gray(frame):
 
 
 def read_yaml_imu(yamlfile):
-    """of_library.py:327-351 (needs the ROS message classes the yaml dump refers to)."""
-    import yaml
-    with open(yamlfile, 'r') as f:
-        imuData = yaml.load(f, Loader=yaml.Loader)
+    """of_library.py:327-351. The dump is parsed with replay.load_ros_yaml: a SafeLoader that rebuilds the ROS
+    messages as inert attribute bags, so neither the ROS classes nor PyYAML's object-constructing loader are needed."""
+    from .replay import load_ros_yaml
+    imuData = load_ros_yaml(yamlfile)
     datastack = []
     for entry in reversed(imuData):
         o, la, av = entry.orientation, entry.linear_acceleration, entry.angular_velocity

@@ -309,10 +309,17 @@ def stream_shard(n_streams, rank, world):
 def gather_stream_velocities(v_local, stream_ids, n_streams, group=None, device=None):
     """Final gather of the per-stream velocities of a sharded fleet (3 doubles per stream): every rank contributes
     its streams' rows to an (n_streams, 3) table, merged with one all-reduce(sum) (rows are disjoint)."""
+    return gather_stream_rows(np.asarray(v_local, dtype=np.float64).reshape(-1, 3), stream_ids, n_streams, group, device)
+
+
+def gather_stream_rows(rows_local, stream_ids, n_streams, group=None, device=None):
+    """(n_local, k) per-stream rows -> (n_streams, k) table on every rank, one all-reduce(sum) over disjoint rows."""
     import torch
     import torch.distributed as dist
-    table = np.zeros((int(n_streams), 3))
-    table[np.asarray(stream_ids, dtype=np.int64)] = np.asarray(v_local, dtype=np.float64).reshape(-1, 3)
+    rows_local = np.asarray(rows_local, dtype=np.float64)
+    rows_local = rows_local.reshape(len(stream_ids), -1) if len(stream_ids) else rows_local.reshape(0, rows_local.shape[-1])
+    table = np.zeros((int(n_streams), rows_local.shape[1]))
+    table[np.asarray(stream_ids, dtype=np.int64)] = rows_local
     t = torch.from_numpy(table)
     if device is not None:
         t = t.to(device)
@@ -335,6 +342,26 @@ def miscentred_points(data, fx=1.27, fy=0.93):
     d[:, 0] = d[:, 0] - np.mean(d[:, 0]) * fx
     d[:, 1] = d[:, 1] - np.mean(d[:, 1]) * fy
     return d
+
+
+def advect_points(data, linear_velocity, angular_velocity, height_above_gr, normal_vector, translation, k, ctx=None):
+    """The dynamic part of the time-evolution sweep (simulation.py:496-499), all k steps in one device launch:
+    step s+1 has data += generate_test_data(data, v, [0,0,0], h, n, t) and h += v.n.
+    -> (pos (k,N,2), true_flow (k,N,2) = generate_test_data(pos_s, v, w, h_s, n, t), heights (k,))."""
+    ctx = ctx or _lib.default_context()
+    d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1, 2)
+    k = int(k)
+    if k < 1:
+        raise ValueError("k must be a positive number of steps")
+    pos = np.zeros((k, len(d), 2)); flow = np.zeros((k, len(d), 2)); hs = np.zeros(k)
+    v3, w3, n3, t3 = _v3(linear_velocity), _v3(angular_velocity), _v3(normal_vector), _v3(translation)
+    h0 = float(np.asarray(height_above_gr, dtype=np.float64).reshape(-1)[0])
+    if len(d):
+        _lib.check(ctx.lib.ofb_advect_points(ctx.h, _lib.ptr(d), len(d), _lib.ptr(v3), _lib.ptr(w3), h0, _lib.ptr(n3),
+                                             _lib.ptr(t3), k, _lib.ptr(pos), _lib.ptr(flow), _lib.ptr(hs)))
+    else:
+        hs[:] = h0 + np.arange(k) * float(v3 @ n3)
+    return pos, flow, hs
 
 
 def _default_sigmas():
@@ -393,13 +420,25 @@ def build_sweep(name, data, k=None):
         k = k or 99; d = miscentred_points(data)
         for i in range(k):
             add(d[:2 * i + 2])
+    elif name == "time_evolution":            # 472-501: points advected by their own flow, height += v.n per step
+        k = k or 100
+        d = np.array(data, dtype=np.float64)
+        d[:, 0] -= np.mean(d[:, 0]); d[:, 1] -= np.mean(d[:, 1])
+        d = d * 10                             # simulation.py:472-474
+        if len(d) > _lib.MC_MAX_POINTS:
+            raise ValueError("time_evolution: at most %d points" % _lib.MC_MAX_POINTS)
+        pos_k, flow_k, h_k = advect_points(d, v, w, h, n, t, k)     # one launch for the k dependent steps
+        sig = _default_sigmas()
+        for i in range(k):
+            pts.append(pos_k[i]); flows.append(flow_k[i])
+            steps.append(make_step(v, w, h_k[i], n, t, len(d), i * len(d), **sig))
     else:
         raise ValueError("unknown sweep %r" % name)
     return steps, np.vstack(pts), np.vstack(flows)
 
 
 SWEEPS = ("flow_errors", "distance_error", "ang_vel_error", "normal_error", "translation_error", "orientation", "height",
-          "point_position", "number_of_points")
+          "point_position", "number_of_points", "time_evolution")
 SWEEP_FILES = {"flow_errors": "effect_of_flow_errors", "distance_error": "effect_of_distance_error",
                "ang_vel_error": "effect_o_ang_vel_error", "normal_error": "effect_of_normal_error",
                "translation_error": "effect_of_translation_error", "orientation": "effect_of_orientation",
@@ -414,3 +453,125 @@ def run_named_sweep(name, data, trials=100, k=None, seed=0, precision="fp32", di
     mean, std, mR, _ = run_sweep(steps, pts, flows, trials, seed=seed, precision=precision, distributed=distributed,
                                  group=group, ctx=ctx)
     return np.append(mean, std), mR
+
+
+# ---- sorting study (simulation.py:604-894): which per-point metric separates moving points / other planes ----------
+def rotate_flows(flow, minang, rng):
+    """simulation.py:702-705 / 767-770 / 858-861: every row turned in the image plane by an angle drawn from
+    U(minang, 2 pi - minang) -- the flows of independently moving points."""
+    out = np.array(flow, dtype=np.float64)
+    for i in range(len(out)):
+        a = rng.uniform(minang, 2 * np.pi - minang)
+        out[i] = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) @ out[i]
+    return out
+
+
+SORTING_KINDS = ("planes", "moving", "moving_and_plane", "dynamic")
+
+
+def sorting_scenario(kind, data, minang=None, rng=None, velocity_scale=None):
+    """Point set, composite true flow and truth of one sorting scenario of the reference:
+      "planes"            simulation.py:615-628  thirds of the points on planes at h = 3, 2, 1 m
+      "moving"            simulation.py:693-706  v x 10; second half: flows rotated (moving points)
+      "moving_and_plane"  simulation.py:753-772  (the LIVE section) h = 2, v x 2.9 h; [0, N/5) static at 2 m,
+                                                 [N/5, 2(N/3)) moving at 1 m, [2(N/3), N) static at 1 m
+      "dynamic"           simulation.py:856-864  one step of the velocity sweep: thirds = static, moving, plane at h + 1;
+                                                 velocity_scale multiplies the module's linear_velocity
+    minang: lower end of the rotation-angle range. The reference writes 10/360*2*np.pi, which Python 2 (the
+    interpreter it ran under) evaluates to 0 -- the default; "dynamic" uses 1 rad (simulation.py:859).
+    -> dict(data, true_flow, linear_velocity, height, groups={name: slice})."""
+    g = globals()
+    rng = rng or np.random.RandomState(0)
+    v = np.array(g["linear_velocity"], dtype=np.float64)
+    w, n, t = g["angular_velocity"], g["normal_vector"], g["translation"]
+    d = np.array(data, dtype=np.float64)
+    N = len(d)
+    gtd = _vel.generate_test_data
+    if kind == "planes":
+        d = centred_points(d)
+        h = 3.0
+        a, b = int(N / 3), 2 * int(N / 3)
+        tf = np.vstack([gtd(d[:a], v, w, h, n, t), gtd(d[a:b], v, w, h - 1, n, t), gtd(d[b:], v, w, h - 2, n, t)])
+        groups = {"3m": slice(0, a), "2m": slice(a, b), "1m": slice(b, N)}
+    elif kind == "moving":
+        d[:, 0] -= np.mean(d[:, 0]); d[:, 1] -= np.mean(d[:, 1])
+        h = float(g["height_above_gr"])
+        v = v * 10
+        a = int(N / 2)
+        tf = np.vstack([gtd(d[:a], v, w, h, n, t), rotate_flows(gtd(d[a:], v, w, h, n, t), 0.0 if minang is None else minang, rng)])
+        groups = {"static": slice(0, a), "moving": slice(a, N)}
+    elif kind == "moving_and_plane":
+        d[:, 0] -= np.mean(d[:, 0]); d[:, 1] -= np.mean(d[:, 1])
+        h = 2.0
+        v = v * 2.9 * h
+        a, b = int(N / 5), 2 * int(N / 3)
+        tf = np.vstack([gtd(d[:a], v, w, h, n, t),
+                        rotate_flows(gtd(d[a:b], v, w, h - 1, n, t), 0.0 if minang is None else minang, rng),
+                        gtd(d[b:], v, w, h - 1, n, t)])
+        groups = {"static_2m": slice(0, a), "moving_1m": slice(a, b), "static_1m": slice(b, N)}
+    elif kind == "dynamic":
+        d[:, 0] -= np.mean(d[:, 0]); d[:, 1] -= np.mean(d[:, 1])
+        h = 1.0
+        v = v * (1.0 if velocity_scale is None else velocity_scale)
+        a, b = int(N / 3), 2 * int(N / 3)
+        tf = np.vstack([gtd(d[:a], v, w, h, n, t), rotate_flows(gtd(d[a:b], v, w, h, n, t), 1.0 if minang is None else minang, rng),
+                        gtd(d[b:], v, w, h + 1, n, t)])
+        groups = {"static": slice(0, a), "moving": slice(a, b), "plane": slice(b, N)}
+    else:
+        raise ValueError("unknown sorting scenario %r (one of %s)" % (kind, ", ".join(SORTING_KINDS)))
+    return dict(data=d, true_flow=tf, linear_velocity=v, height=h, groups=groups)
+
+
+METRICS = ("backward_para", "backward_dist", "forward_para", "forward_dist", "backward_res", "forward_res")
+
+
+def sorting_study(kind, data, iterations=None, seed=0, minang=None, k=100, cumulative=False, ctx=None):
+    """The sorting simulations of simulation.py:604-894 on the GPU (feas_simulation trials + overlap histograms).
+
+    "planes" / "moving" / "moving_and_plane": one feas_simulation over the scenario's composite flow field ->
+        dict with the six per-point means (METRICS), `groups`, and
+        "planes":            sorted_distance, distance_diff (simulation.py:630-631)
+        "moving_and_plane":  sorted_out_forward / sorted_out_backward = the two fractions the live section prints
+                             (parallelity > 0.88 over the middle third, simulation.py:778-779).
+    "dynamic": the velocity sweep of simulation.py:850-877: k steps, step i at linear_velocity * i * 0.05, twelve
+        overlap curves "mov_overlap_<metric>" (static vs moving) and "plane_overlap_<metric>" (static vs the plane one
+        metre further), each (k,). The reference rescales the velocity cumulatively (`linear_velocity=linear_velocity*i*
+        0.05`, which makes it zero from step 0 on); cumulative=True reproduces that, the default sweeps the intended 0..5x."""
+    g = globals()
+    iters = int(g["iterations"] if iterations is None else iterations)
+    rng = np.random.RandomState(int(seed) & 0x7fffffff)
+    w, n, t = g["angular_velocity"], g["normal_vector"], g["translation"]
+    sig = _default_sigmas()
+
+    def run(sc, step_id):
+        return feas_simulation(sc["linear_velocity"], w, sc["height"], n, t, sc["data"], sig["ang_vel_sig"],
+                               sig["translation_sig"], sig["height_sig"], sig["flow_sig"], sig["position_sig"],
+                               sig["normal_sig"], sc["linear_velocity"], iterations=iters, true_flow=sc["true_flow"],
+                               seed=seed, step_id=step_id, ctx=ctx)
+
+    if kind != "dynamic":
+        sc = sorting_scenario(kind, data, minang=minang, rng=rng)
+        out = dict(zip(METRICS, run(sc, 0)))
+        out["groups"] = sc["groups"]
+        out["scenario"] = sc
+        if kind == "planes":
+            out["sorted_distance"] = np.sort(out["forward_dist"])
+            out["distance_diff"] = np.diff(out["sorted_distance"])
+        if kind == "moving_and_plane":
+            third = int(len(sc["data"]) / 3)
+            mid = slice(third, 2 * third)
+            out["sorted_out_forward"] = float(np.sum(out["forward_para"][mid] > 0.88)) / float(third)
+            out["sorted_out_backward"] = float(np.sum(out["backward_para"][mid] > 0.88)) / float(third)
+        return out
+    curves = {("%s_overlap_%s" % (grp, m)): np.zeros(k) for grp in ("mov", "plane") for m in METRICS}
+    scale = 1.0
+    for i in range(k):
+        scale = scale * i * 0.05 if cumulative else i * 0.05
+        sc = sorting_scenario("dynamic", data, minang=minang, rng=rng, velocity_scale=scale)
+        res = dict(zip(METRICS, run(sc, i)))
+        gs = sc["groups"]
+        for m in METRICS:
+            curves["mov_overlap_" + m][i] = overlap(res[m][gs["static"]], res[m][gs["moving"]], ctx=ctx)
+            curves["plane_overlap_" + m][i] = overlap(res[m][gs["static"]], res[m][gs["plane"]], ctx=ctx)
+    curves["velocity_scale"] = np.arange(k) * 0.05
+    return curves

@@ -25,7 +25,9 @@ class StreamTracker:
     topup: "exp"  -> evaluate_exp.py:105-107 (unmasked, maxCorners=max_features, appended),
            "node" -> node:157-172 (circles of mask_radius around surviving points, maxCorners=max_features-count),
            "module" -> of_module.py:83-86 (the set is replaced).
-    gate: None, ("ge", T) (of_module.py:129) or ("le", T) (node:240-245) on of.r_tilde(x, u, n, v_prior, d).
+    gate: None, ("ge", T) (of_module.py:129) or ("le", T) (node:240-245) on of.r_tilde(x, u, n, v_prior, d); the prior is
+          `v_prior` of the step, else the stream's last solved velocity, else `v_init` (node:183 uses [0.1, 0.1, 0.1]);
+          while it is exactly zero the gate is skipped (r_tilde is 1 for every point then).
     max_speed > 0 enables of.static_immobile(new, old, max_speed, d, dummy_value).
     borrow_frames: device-resident grey frames (CUDA tensors) are tracked in place instead of being copied into the
     tracker; pass a NEW tensor every step (the tracker keeps the previous one alive; do not overwrite it)."""
@@ -33,7 +35,7 @@ class StreamTracker:
     def __init__(self, width, height, max_features=100, min_features=20, n_streams=1, feature_params=None,
                  lk_params=None, topup="exp", mask_radius=30, bgr=False, variant="exp", principal=None,
                  scaling=1.0, flow_scaling=None, max_speed=0.0, dummy_value=float("nan"), gate=None, min_solve=3,
-                 min_eig_thr=1e-4, borrow_frames=False, ctx=None):
+                 min_eig_thr=1e-4, borrow_frames=False, v_init=None, ctx=None):
         fp = dict(qualityLevel=0.01, minDistance=10, blockSize=7)
         fp.update(feature_params or {})
         lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 20, 0.03))
@@ -58,6 +60,8 @@ class StreamTracker:
             cfg.gate_T = float(gate[1])
         cfg.min_solve = int(min_solve)
         cfg.borrow_frames = 1 if borrow_frames else 0
+        if v_init is not None:       # the node's self.vel = [0.1, 0.1, 0.1] (velocity_measurment_node:183)
+            cfg.v_init[:] = [float(x) for x in np.asarray(v_init, dtype=np.float64).reshape(3)]
         self._held = []          # borrow_frames: the last two device frames stay referenced until they are no longer read
         self.cfg = cfg
         self.n_streams, self.width, self.height, self.bgr = int(n_streams), int(width), int(height), bool(bgr)
@@ -199,28 +203,28 @@ class FleetTracker:
         return out
 
     def gather_velocities(self):
-        """(n_streams, 3) velocities of the last step on every rank; rows of streams that did not solve are NaN."""
-        from .simulation import gather_stream_velocities
+        """(n_streams, 3) velocities of the last step on every rank; rows of streams that did not solve (or have not
+        stepped yet) are NaN. One all-reduce of an (n_streams, 4) table: velocity + a validity column (NaN cannot ride
+        a sum)."""
+        from .simulation import gather_stream_rows
         import torch.distributed as dist
-        v = np.zeros((len(self.streams), 3))
+        rows = np.zeros((len(self.streams), 4))
         if self.last is not None:
-            v = np.where((self.last["flags"] & _lib.TRACK_SOLVED)[:, None] != 0, self.last["v"], np.nan)
+            ok = (self.last["flags"] & _lib.TRACK_SOLVED) != 0
+            rows[:, :3] = np.where(ok[:, None], self.last["v"], 0.0)
+            rows[:, 3] = ok
         if self.world == 1:
-            table = np.full((self.n_streams, 3), np.nan)
-            table[self.streams] = v
-            return table
-        dev = None
-        if dist.get_backend(self.group) == "nccl":
-            import torch
-            dev = torch.device("cuda", self.local.ctx.device if self.local is not None else 0)
-        # NaN rows cannot ride a sum: send a validity column alongside
-        ok = ~np.isnan(v[:, 0])
-        vv = np.where(ok[:, None], v, 0.0)
-        table = gather_stream_velocities(vv, self.streams, self.n_streams, self.group, dev)
-        valid = gather_stream_velocities(np.repeat(ok[:, None].astype(float), 3, axis=1), self.streams, self.n_streams,
-                                         self.group, dev)
-        table[valid[:, 0] == 0] = np.nan
-        return table
+            table = rows
+        else:
+            dev = None
+            if dist.get_backend(self.group) == "nccl":
+                # a rank that owns no stream still takes part in the collective, from ITS OWN GPU
+                import torch
+                dev = torch.device("cuda", self.local.ctx.device if self.local is not None else torch.cuda.current_device())
+            table = gather_stream_rows(rows, self.streams, self.n_streams, self.group, dev)
+        out = table[:, :3].copy()
+        out[table[:, 3] == 0] = np.nan
+        return out
 
     def close(self):
         if self.local is not None:

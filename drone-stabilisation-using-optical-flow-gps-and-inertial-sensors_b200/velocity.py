@@ -4,6 +4,7 @@ with their positional signatures and return tuples, backed by libofb200.so.
     solve_lgs(x,u,d,n,omega)        velocity_measurment_node:30-42      -> (v, res, rank, s)
     solve_lgs(x,u,d,n,omega,t)      numerical_simulation/simulation.py:15-30 -> (v, res, s)
     solve_lgs(..., variant='exp')   flight_experiments/evaluate_exp.py:18-31 -> (v, res)
+    solve_lgs_module(x,u,n,dist)    optical_flow_experiments/of_module.py:136-146 (inline lstsq) -> (v, res, rank, s)
     generate_test_data(x,v,omega,d,n[,t])   node:25-29 / simulation.py:7-12
     feasibility(position,linear_velocity,flow,angular_velocity,translation,normal)  simulation.py:108-120
 """
@@ -71,6 +72,41 @@ def solve_lgs(x, u, d, n, omega, t=None, variant=None, ctx=None):
     return v, res, s
 
 
+def solve_lgs_module(x, u, n, dist=None, v_prior=None, ctx=None):
+    """The inline system of optical_flow_experiments/of_module.py:136-146, `np.linalg.lstsq(A, B)` with
+    A_i = [X_i]x / dist_i and B_i = A_i u_i / (n . X_i) -> (v_obs, R, rank, s) as lstsq returns them.
+    x, u: (N,2), or the homogeneous (N,3) rows (x, y, 1) / (ux, uy, 0) of of_module.py:96-108. dist: the per-point
+    `distance` output of the 4-argument of.r_tilde (of_module.py:125); when omitted it is derived on the device from
+    v_prior exactly as that r_tilde does."""
+    ctx = ctx or _lib.default_context()
+    x = np.asarray(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    if x.ndim == 3 and x.shape[1] == 1:
+        x = x.reshape(len(x), -1)
+        u = u.reshape(len(u), -1)
+    if x.ndim != 2 or x.shape[1] not in (2, 3) or u.shape != x.shape:
+        raise ValueError("x and u must both have shape (N,2) or (N,3)")
+    x, u = np.ascontiguousarray(x), np.ascontiguousarray(u)
+    if dist is None and v_prior is None:
+        raise ValueError("solve_lgs_module needs the per-point distances or the prior velocity they derive from")
+    dd = None
+    if dist is not None:
+        dd = np.ascontiguousarray(np.asarray(dist, dtype=np.float64).reshape(-1))
+        if len(dd) != len(x):
+            raise ValueError("one distance per point is required")
+    n3 = _vec3(n, "n")
+    vp = _vec3(v_prior, "v_prior") if v_prior is not None else None
+    v = np.zeros(3)
+    s = np.zeros(3)
+    res = C.c_double(0.0)
+    rank = C.c_int(0)
+    _lib.check(ctx.lib.ofb_solve_velocity_module(ctx.h, _lib.ptr(x), _lib.ptr(u), len(x), x.shape[1], _lib.ptr(dd),
+                                                 _lib.ptr(n3), _lib.ptr(vp), _lib.ptr(v), C.addressof(res),
+                                                 C.addressof(rank), _lib.ptr(s)))
+    r = np.array([res.value]) if (rank.value == 3 and 3 * len(x) > 3) else np.array([])
+    return v, r, rank.value, s
+
+
 def solve_lgs_batched(x, u, offsets, d, n, omega, t=None, variant="node", ctx=None):
     """Many frames at once: frame f uses rows offsets[f]:offsets[f+1]. Returns v (F,3), res (F,), rank (F,), s (F,3)."""
     ctx = ctx or _lib.default_context()
@@ -78,6 +114,10 @@ def solve_lgs_batched(x, u, offsets, d, n, omega, t=None, variant="node", ctx=No
     u = _pts(u, "u")
     offsets = np.ascontiguousarray(offsets, dtype=np.int32)
     F = len(offsets) - 1
+    if F < 1 or offsets[0] < 0 or np.any(np.diff(offsets) < 0):
+        raise ValueError("offsets must be a non-decreasing sequence of at least two non-negative row indices")
+    if len(x) != len(u) or len(x) < offsets[-1]:
+        raise ValueError("x and u must have the same number of rows, at least offsets[-1] = %d" % offsets[-1])
     d = np.ascontiguousarray(np.broadcast_to(np.asarray(d, dtype=np.float64).reshape(-1), (F,)))
     n3 = np.ascontiguousarray(np.broadcast_to(np.asarray(n, dtype=np.float64), (F, 3)))
     w3 = np.ascontiguousarray(np.broadcast_to(np.asarray(omega, dtype=np.float64), (F, 3)))

@@ -183,7 +183,7 @@ def make_pair_cfg(width, height, max_corners, quality=0.01, min_distance=10.0, b
     cfg.win_w, cfg.win_h = int(win[0]), int(win[1])
     cfg.max_count, cfg.eps = _criteria(criteria)
     cfg.min_eig_thr = float(min_eig_thr)
-    cfg.variant = _lib.VARIANTS[variant]
+    cfg.variant = _lib.TRACKER_VARIANTS[variant]       # 'module' is accepted by the tracker only (the C side checks)
     c = principal if principal is not None else pix_trans((width, height))
     cfg.cx, cfg.cy = float(c[0]), float(c[1])
     cfg.pos_scale, cfg.flow_scale = float(pos_scale), float(flow_scale)
@@ -191,10 +191,13 @@ def make_pair_cfg(width, height, max_corners, quality=0.01, min_distance=10.0, b
     return cfg
 
 
-def frame_pairs(prev, nxt, imu, cfg, pts_in=None, n_in=None, want_tracks=False, ctx=None):
+def frame_pairs(prev, nxt, imu, cfg, pts_in=None, n_in=None, want_tracks=False, ctx=None, on_overflow="raise"):
     """Batched detect(+)track+solve. prev/nxt: (N,H,W) uint8 numpy arrays (host) or CUDA tensors;
     imu: structured array _lib.IMU_DTYPE (N,). Returns a structured array _lib.RESULT_DTYPE (N,)
-    (and prev_pts, next_pts, status when want_tracks)."""
+    (and prev_pts, next_pts, status when want_tracks).
+    A pair whose detector ran out of candidate slots (plateau images: more than w*h/4 + 1024 local maxima above the
+    quality threshold) carries `flags & PAIR_OVERFLOW`; its feature list is truncated, so by default that raises
+    OfbError (on_overflow="ignore" returns the flagged records instead)."""
     ctx = ctx or _lib.default_context()
     n = int(prev.shape[0])
     h, w = int(prev.shape[1]), int(prev.shape[2])
@@ -219,17 +222,21 @@ def frame_pairs(prev, nxt, imu, cfg, pts_in=None, n_in=None, want_tracks=False, 
     _lib.check(ctx.lib.ofb_frame_pairs(ctx.h, C.byref(cfg), n, _lib.ptr(prev), _lib.ptr(nxt), w, w * h, _lib.ptr(imu),
                                        _lib.ptr(pts_in), _lib.ptr(n_in), _lib.ptr(res), _lib.ptr(pp), _lib.ptr(pn),
                                        _lib.ptr(st)))
+    if on_overflow == "raise" and (res["flags"] & _lib.PAIR_OVERFLOW).any():
+        bad = np.nonzero(res["flags"] & _lib.PAIR_OVERFLOW)[0]
+        raise _lib.OfbError("frame_pairs: detector candidate buffer overflowed for pair(s) %s: the image has more than "
+                            "w*h/4 + 1024 local maxima above the quality threshold (plateaus)" % bad[:8].tolist())
     if want_tracks:
         return res, pp, pn, st
     return res
 
 
-def frame_sequence(frames, imu, cfg, want_tracks=False, ctx=None):
+def frame_sequence(frames, imu, cfg, want_tracks=False, ctx=None, on_overflow="raise"):
     """One camera stream: frames (N+1,H,W) uint8 -> N consecutive pairs (frame i, frame i+1), as
     velocity_measurment_node:224-267 sees them (it keeps the previous callback's image). Passing the two views
     of ONE buffer lets the library upload every frame and build its pyramid once (`next == prev + image_stride`
     is the C ABI's sequence layout, include/ofb200.h)."""
     if isinstance(frames, np.ndarray):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
-    return frame_pairs(frames[:-1], frames[1:], imu, cfg, want_tracks=want_tracks, ctx=ctx)
+    return frame_pairs(frames[:-1], frames[1:], imu, cfg, want_tracks=want_tracks, ctx=ctx, on_overflow=on_overflow)
 

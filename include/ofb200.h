@@ -120,6 +120,11 @@ int ofb_pyrlk(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image, const ofb_pyr* 
 #define OFB_VARIANT_NODE 0
 #define OFB_VARIANT_EXP  1
 #define OFB_VARIANT_SIM  2
+#define OFB_VARIANT_MODULE 3   /* the inline system of optical_flow_experiments/of_module.py:136-146: rows [X]x / dist_i,
+                                  rhs [X]x u3 / (dist_i (n.X)) with a per-point distance dist_i from the older 4-argument
+                                  of.r_tilde (of_module.py:125); no gyro term, no common height, no lever arm. Accepted by
+                                  ofb_solve_velocity_module and by the tracker (ofb_tracker_cfg.pair.variant), where dist_i
+                                  comes from the step's prior velocity. */
 int ofb_solve_velocity(ofb_ctx* ctx, int variant, const double* x, const double* u, int n, double d,
                        const double n3[3], const double w3[3], const double t3[3],
                        double v_out[3], double* res, int* rank, double s_out[3]);
@@ -127,9 +132,22 @@ int ofb_solve_velocity_batched(ofb_ctx* ctx, int variant, const double* x, const
                                const int* offsets, int n_frames,
                                const double* d, const double* n3, const double* w3, const double* t3,
                                double* v_out, double* res, int* rank, double* s_out);
+/* Variant MODULE (of_module.py:136-146): np.linalg.lstsq(A, B) with A_i = [X_i]x / dist_i and
+ * B_i = A_i u_i / (n . X_i). x,u: n x ld doubles (ld = 2, or 3 for the homogeneous rows (x, y, 1) / (ux, uy, 0) the
+ * reference builds at of_module.py:96-108). dist: n per-point distances (the `distance` output of the 4-argument
+ * of.r_tilde); when NULL they are derived from v_prior[3] exactly as that r_tilde does (an all-zero prior, for which
+ * the reference would divide by zero, gives unit distances). Outputs as ofb_solve_velocity. */
+int ofb_solve_velocity_module(ofb_ctx* ctx, const double* x, const double* u, int n, int ld, const double* dist,
+                              const double n3[3], const double* v_prior,
+                              double v_out[3], double* res, int* rank, double s_out[3]);
 /* generate_test_data: simulation.py:7-12 (t3 != NULL) / velocity_measurment_node:25-29 (t3 NULL) */
 int ofb_generate_flow(ofb_ctx* ctx, const double* x, int n, const double v3[3], const double w3[3],
                       double d, const double n3[3], const double* t3, double* u_out);
+/* Time-evolution sweep driver (simulation.py:472-501): k steps of `data += generate_test_data(data, v, 0, h, n, t);
+ * h += v.n`. pos_out[k][n][2] = the points of every step, flow_out[k][n][2] (may be NULL) = the step's true flow
+ * generate_test_data(data_s, v, w, h_s, n, t), d_out[k] (may be NULL) = the heights h_s. One launch for all k steps. */
+int ofb_advect_points(ofb_ctx* ctx, const double* x0, int n, const double v3[3], const double w3[3], double d0,
+                      const double n3[3], const double t3[3], int k, double* pos_out, double* flow_out, double* d_out);
 /* r_tilde: of_library.py:365-386. x,u are n x ld doubles (ld = 2, or 3 for the homogeneous 4-arg
  * copy in sensor_precision_experiments/pixhawk_pure_IMU/of_library.py:365-384, then dist is ignored
  * when <= 0). Outputs r[n], d_out[n]. */
@@ -164,6 +182,9 @@ typedef struct {   /* per pair IMU/sonar sample */
     double t[3];     /* lever arm (EXP/SIM variants) */
 } ofb_imu_sample;
 
+#define OFB_PAIR_OVERFLOW 2        /* ofb_pair_result.flags: the detector's candidate buffer (w*h/4 + 1024 local maxima
+                                      per image) overflowed -- plateau images; the feature list of this pair is
+                                      truncated and must not be trusted (same bit as OFB_TRACK_OVERFLOW) */
 typedef struct {
     double v[3];
     double s[3];
@@ -171,6 +192,7 @@ typedef struct {
     int    rank;
     int    n_features;   /* detected (or given) */
     int    n_tracked;    /* status==1 */
+    int    flags;        /* OFB_PAIR_* (occupies what used to be tail padding: the record is still 72 bytes) */
 } ofb_pair_result;
 
 /* prev/next: n_pairs images each, image i at base + i*image_stride (host or device).
@@ -229,6 +251,9 @@ typedef struct {
     int    borrow_frames;    /* 1: device-resident grey frames are used in place instead of being copied into the
                                 tracker; the caller keeps frame k unchanged until step k+1 has completed (a ring of
                                 two buffers per stream is enough). Ignored for host or BGR frames. */
+    double v_init[3];        /* prior velocity of the r_tilde gate before the first solve (velocity_measurment_node:183
+                                starts from self.vel = [0.1, 0.1, 0.1]). While the prior is exactly zero (no v_init, no
+                                v_prior, nothing solved yet) the gate is skipped: r_tilde is 1 for every point then. */
 } ofb_tracker_cfg;
 
 typedef struct {
@@ -256,7 +281,7 @@ int ofb_tracker_capacity(const ofb_tracker* trk, int* capacity_out);
 int ofb_tracker_set_points(ofb_tracker* trk, const float* pts, const int* counts);
 /* frames: n_streams images (grey u8, or BGR8 when bgr_input), image i at frames + i*image_stride, host or
  * device; imu: one sample per stream; v_prior: n_streams x 3 prior velocity for the r_tilde gate (NULL = the
- * stream's last solved velocity, zeros before the first solve). Outputs (host or device; optional ones may be
+ * stream's last solved velocity, cfg.v_init before the first solve; an all-zero prior skips the gate). Outputs (host or device; optional ones may be
  * NULL): results[n_streams]; pts_out n_streams x capacity x 2 and n_out[n_streams] = point sets after the step;
  * kept_prev / kept_next n_streams x capacity x 2 = the (old, new) positions the solve used (first n_kept). */
 int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t image_stride,

@@ -13,6 +13,9 @@ reference lines it follows (paths relative to /root/reference):
                                                stream can be replayed trial by trial)
 * feas_simulation trial simulation.py:70-104
 * overlap              simulation.py:124-136
+* solve_lgs_module     optical_flow_experiments/of_module.py:136-146 (the inline per-point-distance system)
+* advect_points        simulation.py:496-499 (time-evolution sweep: points move by their own flow)
+* sorting_scenario_live simulation.py:753-772 (the live sorting scenario: static / moving / parallel-plane points)
 * pix_trans            of_library.py:31-43
 * quaternion -> R, n   velocity_measurment_node:65-70
 * body -> world        velocity_measurment_node:258
@@ -93,6 +96,58 @@ def solve_lgs(x, u, d, n, omega, t=None, variant=None):
     if t is not None and variant != "node":
         v = v - np.cross(np.asarray(omega, dtype=np.float64), np.asarray(t, dtype=np.float64))
     return v, res, rank, s
+
+
+def solve_lgs_module(x, u, n, dist):
+    """optical_flow_experiments/of_module.py:136-146: A_i = [X_i]x / dist_i, B_i = A_i u_i / (n . X_i),
+    np.linalg.lstsq(A, B) -> (v_obs, R, rank, s). x, u: (N,3) homogeneous rows (x, y, 1) / (ux, uy, 0), or (N,2)."""
+    x = np.asarray(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    if x.shape[1] == 2:
+        x = np.hstack([x, np.ones((len(x), 1))])
+        u = np.hstack([u, np.zeros((len(u), 1))])
+    n = np.asarray(n, dtype=np.float64)
+    A = np.zeros((3 * len(x), 3))
+    B = np.zeros(3 * len(x))
+    for i in range(len(x)):
+        ai = np.array([[0.0, -1.0, x[i, 1]], [1.0, 0.0, -x[i, 0]], [-x[i, 1], x[i, 0], 0.0]]) / dist[i]
+        A[3 * i:3 * i + 3] = ai
+        B[3 * i:3 * i + 3] = np.dot(ai, u[i]) / np.dot(n, x[i])
+    v, res, rank, sv = np.linalg.lstsq(A, B, rcond=None)
+    return v, res, rank, sv
+
+
+def advect_points(data, linear_velocity, height, normal, translation, k):
+    """simulation.py:496-499, k steps: data += generate_test_data(data, v, [0,0,0], h, n, t); h += v . n.
+    -> (positions (k,N,2), heights (k,)) at the START of every step."""
+    d = np.array(data, dtype=np.float64)
+    h = float(height)
+    pos, hs = [], []
+    for _ in range(k):
+        pos.append(d.copy()); hs.append(h)
+        d = d + generate_test_data(d, linear_velocity, np.zeros(3), h, normal, translation)
+        h = h + float(np.dot(linear_velocity, normal))
+    return np.array(pos), np.array(hs)
+
+
+def sorting_scenario_live(data, linear_velocity, angular_velocity, normal, translation, angles):
+    """simulation.py:753-772: centred points, h = 2, v x 2.9 h; [0, N/5) static at 2 m, [N/5, 2(N/3)) at 1 m with their
+    flows rotated by `angles` (one per row, the reference draws them from U(minang, 2 pi - minang)), [2(N/3), N) at 1 m.
+    -> (data, true_flow, linear_velocity, height)."""
+    d = np.array(data, dtype=np.float64)
+    d[:, 0] = d[:, 0] - np.mean(d[:, 0])
+    d[:, 1] = d[:, 1] - np.mean(d[:, 1])
+    h = 2.0
+    v = np.asarray(linear_velocity, dtype=np.float64) * 2.9 * h
+    N = len(d)
+    a, b = int(N / 5), 2 * int(N / 3)
+    first = generate_test_data(d[:a], v, angular_velocity, h, normal, translation)
+    second = generate_test_data(d[a:b], v, angular_velocity, h - 1, normal, translation)
+    for i in range(len(second)):
+        c, s_ = np.cos(angles[i]), np.sin(angles[i])
+        second[i] = np.dot(np.array([[c, -s_], [s_, c]]), second[i])
+    third = generate_test_data(d[b:], v, angular_velocity, h - 1, normal, translation)
+    return d, np.vstack([first, second, third]), v, h
 
 
 def r_tilde(x, u, n, v, dist=None):

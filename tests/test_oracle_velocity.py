@@ -118,3 +118,58 @@ def test_oracle_against_live_reference():
                                    sim["generate_test_data"](x, np.array([1.0, 2, 3]), w, d, n, t), atol=1e-13)
         np.testing.assert_allclose(vo.feasibility(x, [1, 2, 3], u, w, t, n),
                                    sim["feasibility"](x, np.array([1.0, 2, 3]), u, w, t, n), rtol=1e-12)
+
+
+# ---- round 2: of_module's inline system, the time-evolution sweep, the live sorting scenario -----------------
+@pytest.fixture(scope="module")
+def g2():
+    return np.load(os.path.join(GOLDEN, "velocity_golden_r2.npz"))
+
+
+def test_module_system_matches_reference(g2):
+    """oracle.solve_lgs_module == the statements of of_module.py:136-146 exec'd unmodified (golden), with the
+    distances of the reference's own 4-argument r_tilde."""
+    for c in range(int(g2["module_n_cases"])):
+        k = lambda s: g2["module%d_%s" % (c, s)]
+        r, dist = vo.r_tilde(k("x"), k("u"), k("n"), k("v_prior"))
+        np.testing.assert_allclose(dist, k("dist"), rtol=1e-12)
+        np.testing.assert_allclose(r, k("feas"), atol=1e-12)
+        v, res, rank, s = vo.solve_lgs_module(k("x"), k("u"), k("n"), k("dist"))
+        np.testing.assert_allclose(v, k("v"), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(s, k("s"), rtol=1e-10)
+        assert rank == int(k("rank"))
+        np.testing.assert_allclose(res, k("res"), rtol=1e-6, atol=1e-18)
+
+
+def test_time_evolution_trajectory_matches_reference(g2):
+    """oracle.advect_points == the trajectory the reference's commented time-analysis block (simulation.py:472-499)
+    printed when its statements were exec'd."""
+    pos, hs = vo.advect_points(g2["te_pos"][0], [1, 1, 1], 1.0, [0, 0, 1], [0.02, 0, 0.205], 100)
+    np.testing.assert_allclose(hs, g2["te_heights"], rtol=0, atol=0)
+    np.testing.assert_allclose(pos, g2["te_pos"], rtol=1e-12, atol=1e-9)
+    last = pos[-1] + vo.generate_test_data(pos[-1], [1, 1, 1], np.zeros(3), hs[-1], [0, 0, 1], [0.02, 0, 0.205])
+    np.testing.assert_allclose(last, g2["te_final_pos"], rtol=1e-12, atol=1e-9)
+
+
+def test_live_sorting_scenario_matches_reference(g2, points200):
+    """oracle.sorting_scenario_live == what the live statements simulation.py:753-772 built (points, composite flow)."""
+    d, tf, v, h = vo.sorting_scenario_live(points200, [1, 1, 1], [1, 1, 1], [0, 0, 1], [0.02, 0, 0.205], g2["live_angles"])
+    np.testing.assert_allclose(d, g2["live_data"], atol=1e-13)
+    np.testing.assert_allclose(v, g2["live_velocity"], rtol=1e-15)
+    assert h == float(g2["live_height"]) == 2.0
+    np.testing.assert_allclose(tf, g2["live_true_flow"], rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference")
+def test_module_system_live_reference():
+    """Where the reference exists: regenerate one module case through the AST-extracted statements and compare."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_r2", os.path.join(os.path.dirname(GOLDEN), "..", "tools",
+                                                                               "make_golden_r2.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = {}
+    mod.module_golden(g)
+    for c in range(int(g["module_n_cases"])):
+        v, res, rank, s = vo.solve_lgs_module(g["module%d_x" % c], g["module%d_u" % c], g["module%d_n" % c], g["module%d_dist" % c])
+        np.testing.assert_allclose(v, g["module%d_v" % c], rtol=1e-9, atol=1e-12)
