@@ -33,6 +33,8 @@ def lib():
         L.orc_pyr_down.restype = None
         L.orc_min_eig_map.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p]
         L.orc_min_eig_map.restype = None
+        L.orc_min_eig_map_fp32sum.argtypes = L.orc_min_eig_map.argtypes
+        L.orc_min_eig_map_fp32sum.restype = None
         L.orc_select_features.argtypes = [f32p, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_double, ctypes.c_double, f32p, ctypes.c_int]
         L.orc_select_features.restype = ctypes.c_int
@@ -79,11 +81,13 @@ def build_pyramid(img, max_level):
     return levels
 
 
-def min_eig_map(img, block_size):
+def min_eig_map(img, block_size, fp32_sums=False):
+    """cornerMinEigenVal from EXACT integer window sums (default), or with OpenCV-style fp32 accumulation."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w = img.shape
     eig = np.empty((h, w), np.float32)
-    lib().orc_min_eig_map(_u8(img), w, h, w, block_size, _f32(eig))
+    fn = lib().orc_min_eig_map_fp32sum if fp32_sums else lib().orc_min_eig_map
+    fn(_u8(img), w, h, w, block_size, _f32(eig))
     return eig
 
 

@@ -70,10 +70,55 @@ ORC_API void orc_pyr_down(const uint8_t* src, int w, int h, int pitch, uint8_t* 
 }
 
 /* ---- cornerMinEigenVal, aperture 3, u8 input (App. B.5) ---------------------------
- * fp32 pipeline in OpenCV's operation order: scaled Sobel -> products -> box SUM -> lambda_min.
- * Window sums are taken directly (OpenCV uses a running column sum): documented <= few ulp.
+ * OpenCV: scaled Sobel -> products -> box SUM (reflect-101 on the product images) -> lambda_min, all in fp32 with a
+ * running column sum. The Sobel outputs are integers, so the products and the blockSize x blockSize window sums are
+ * integers too (< 2^31 for blockSize <= 45): orc_min_eig_map takes them EXACTLY and rounds only where the result is
+ * formed -- a = (float)Sxx * (scale^2/2), b = (float)Sxy * scale^2, c = (float)Syy * (scale^2/2),
+ * (a + c) - sqrt((a - c)^2 + b^2) -- which makes the map independent of the summation order (and symmetric wherever
+ * the window sums are, e.g. rows 0 and 1 for an even blockSize, as OpenCV's own running sums happen to be). It differs
+ * from OpenCV's fp32 accumulation by its summation noise, a few ulp of a + c ("documented float tie").
+ * orc_min_eig_map_fp32sum keeps the plain fp32 accumulation (window order) for comparison.
  */
 ORC_API void orc_min_eig_map(const uint8_t* src, int w, int h, int pitch, int block_size, float* eig)
+{
+    const float scale = (float)(1.0 / (4.0 * 255.0 * block_size));
+    const float scale2 = scale * scale, h2 = 0.5f * scale2;
+    const int bs = block_size, a0 = bs / 2;
+    const int pw = w + bs, ph = h + bs;                     /* padded product images + one zero row/column */
+    long long* I = (long long*)calloc((size_t)3 * (pw + 1) * (ph + 1), sizeof(long long));
+    long long* Ixx = I; long long* Ixy = I + (size_t)(pw + 1) * (ph + 1); long long* Iyy = Ixy + (size_t)(pw + 1) * (ph + 1);
+    /* integral images of the products at the reflected POSITIONS y - a0 + j, x - a0 + i */
+    for (int py = 0; py < ph - 1; ++py) {
+        const int y = refl101(py - a0, h);
+        const uint8_t* r0 = src + (size_t)refl101(y - 1, h) * pitch;
+        const uint8_t* r1 = src + (size_t)y * pitch;
+        const uint8_t* r2 = src + (size_t)refl101(y + 1, h) * pitch;
+        long long rxx = 0, rxy = 0, ryy = 0;
+        for (int px = 0; px < pw - 1; ++px) {
+            const int x = refl101(px - a0, w);
+            const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
+            const int gx = (r0[xp] - r0[xm]) + 2 * (r1[xp] - r1[xm]) + (r2[xp] - r2[xm]);
+            const int gy = (r2[xm] + 2 * r2[x] + r2[xp]) - (r0[xm] + 2 * r0[x] + r0[xp]);
+            rxx += (long long)gx * gx; rxy += (long long)gx * gy; ryy += (long long)gy * gy;
+            const size_t o = (size_t)(py + 1) * (pw + 1) + (px + 1), up = o - (pw + 1);
+            Ixx[o] = Ixx[up] + rxx; Ixy[o] = Ixy[up] + rxy; Iyy[o] = Iyy[up] + ryy;
+        }
+    }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const size_t o00 = (size_t)y * (pw + 1) + x, o01 = o00 + bs, o10 = o00 + (size_t)bs * (pw + 1), o11 = o10 + bs;
+            const int sxx = (int)(Ixx[o11] - Ixx[o01] - Ixx[o10] + Ixx[o00]);
+            const int sxy = (int)(Ixy[o11] - Ixy[o01] - Ixy[o10] + Ixy[o00]);
+            const int syy = (int)(Iyy[o11] - Iyy[o01] - Iyy[o10] + Iyy[o00]);
+            const float a = (float)sxx * h2, b = (float)sxy * scale2, c = (float)syy * h2;
+            const float dac = a - c;
+            const float t1 = dac * dac, t2 = b * b;
+            eig[(size_t)y * w + x] = (a + c) - sqrtf(t1 + t2);
+        }
+    free(I);
+}
+
+ORC_API void orc_min_eig_map_fp32sum(const uint8_t* src, int w, int h, int pitch, int block_size, float* eig)
 {
     float scale = (float)(1.0 / (4.0 * 255.0 * block_size));
     float* dxx = (float*)malloc(sizeof(float) * 3 * (size_t)w * h);
