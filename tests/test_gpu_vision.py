@@ -306,6 +306,9 @@ def test_two_kernel_variants_agree(ctx):
                             ofb200.goodFeaturesToTrack(img, 300, 0.01, 7, blockSize=bs, ctx=ctx),
                             ofb200.goodFeaturesToTrack(img, 0, 0.05, 3, mask=mask, blockSize=bs, ctx=ctx))
             fast, pts_fast, ptsm_fast = both()                      # marching kernel for blockSize 3, 7, 12
+            v1, pts_v1, ptsm_v1 = with_env("OFB_EIG_MARCH_V1", both)  # ... with its general row loop on every strip
+            assert np.array_equal(fast, v1) and np.array_equal(as_list(pts_fast), as_list(pts_v1))
+            assert np.array_equal(as_list(ptsm_fast), as_list(ptsm_v1))
             tile, pts_tile, ptsm_tile = with_env("OFB_EIG_TILE", both)
             gen, pts_gen, ptsm_gen = with_env("OFB_EIG_GENERIC", both)
             assert np.array_equal(fast, tile), (h, w, bs, np.abs(fast - tile).max(), np.argwhere(fast != tile)[:5])
@@ -336,6 +339,36 @@ def test_two_kernel_variants_agree(ctx):
             on, os_, oe = io.pyrlk(a, b, pts, win, 3, (3, 20, 0.03))
             assert np.array_equal(s1, os_)
             assert np.abs(n1 - on)[ok].max() <= 5e-3
+
+
+def test_marching_fast_rows_at_full_size(ctx):
+    """The lean row loop of the marching kernel (interior strips) against its general row loop at 1080p and at a size whose
+    band count / band height parity differs: identical maps, identical candidate-derived lists, with and without
+    a batch (bands get shorter as the batch grows)."""
+    import ofb200
+    for (h, w), seed, bs in [((1080, 1920), 71, 7), ((721, 1283), 72, 7), ((540, 960), 73, 3), ((487, 1001), 74, 12)]:
+        img = synth.texture(h, w, seed)
+        run = lambda: (ofb200.cornerMinEigenVal(img, bs, ctx=ctx), ofb200.goodFeaturesToTrack(img, 1000, 0.01, 10, blockSize=bs, ctx=ctx))
+        fast_map, fast_pts = run()
+        os.environ["OFB_EIG_MARCH_V1"] = "1"
+        try:
+            ref_map, ref_pts = run()
+        finally:
+            os.environ["OFB_EIG_MARCH_V1"] = "0"
+        assert np.array_equal(fast_map, ref_map), (h, w, bs, np.argwhere(fast_map != ref_map)[:4])
+        assert np.array_equal(as_list(fast_pts), as_list(ref_pts)), (h, w, bs)
+    # batches: 1, 3 and 9 images of 720p through the fused path (feature lists per image must not depend on the batch)
+    a, b, mo = synth.make_pair(720, 1280, 1, 77)
+    cfg = ofb200.make_pair_cfg(1280, 720, 300, 0.01, 10, 7, (15, 15), 3, (3, 20, 0.03), variant="node",
+                               principal=(mo["cx"], mo["cy"]), pos_scale=1.0 / mo["f"], flow_scale=1.0 / (mo["f"] * mo["dt"]))
+    lists = []
+    for nb in (1, 3, 9):
+        imu = np.zeros(nb, ofb200._lib.IMU_DTYPE); imu["d"][:], imu["n"][:], imu["w"][:] = mo["d"], mo["n"], mo["w"]
+        res, pp, pn, st = ofb200.frame_pairs(np.stack([a] * nb), np.stack([b] * nb), imu, cfg, want_tracks=True, ctx=ctx)
+        for i in range(nb):
+            lists.append(pp[i, :int(res["n_features"][i])])
+    for l in lists[1:]:
+        assert np.array_equal(l, lists[0])
 
 
 def test_marching_kernel_shapes_vs_generic(ctx):
