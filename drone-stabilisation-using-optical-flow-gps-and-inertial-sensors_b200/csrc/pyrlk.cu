@@ -490,6 +490,231 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
     }
 }
 
+// ================= register-resident kernel, second generation ===========================================
+// Same mapping and the same integer arithmetic as lk_track_fast_kernel (which stays as the cross-check, OFB_LK_V1=1);
+// what changed is what its per-source-line profile flagged (profiles/r2_before_lk_by_line.txt: 7.0 k warp
+// instructions per feature, ~920 per pyramid level before the first Newton step):
+//   * Scharr under the window with two columns per instruction (packed 16-bit halves, biased so that no half ever
+//     borrows from its neighbour) instead of 33 byte extractions and scalar arithmetic per level; the gradients stay
+//     biased by +4096 through the bilinear interpolation, whose weights sum to exactly 2^14, so the bias leaves in the
+//     rounding constant;
+//   * the row below comes through 10 shuffles of column PAIRS (was 9 shuffles of packed (gx, gy) words plus their
+//     packing and unpacking);
+//   * the template value uses the dp2a taps of the Newton loop (no byte extraction at all);
+//   * per-level parameters are one packed record in constant memory, the level scale is built from its exponent, and
+//     the convergence test |delta|^2 <= eps^2 is decided in fp32 unless it falls within 1e-6 of the threshold (the fp64
+//     evaluation OpenCV uses is only needed there).
+__device__ __forceinline__ unsigned int prmt(unsigned int a, unsigned int b, unsigned int sel) { return __byte_perm(a, b, sel); }
+
+__global__ void __launch_bounds__(LKF_WARPS * 32, 8)
+lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                      uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
+                      int counts_stride, int n_uniform, size_t pts_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.y;
+    const int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
+    const int feat = blockIdx.x * LKF_WARPS + (threadIdx.x >> 5);
+    if (feat >= n) return;
+    const int winW = P.win_w, winH = P.win_h;
+    const int r = lane >> 1, hh = lane & 1;
+    const size_t po = (size_t)pair * pts_stride + feat;
+    const float ptx = prev_pts[2 * po], pty = prev_pts[2 * po + 1];
+    float nx = 0.f, ny = 0.f;
+    if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = next_pts[2 * po]; ny = next_pts[2 * po + 1]; }
+    const float hwx = P.hwx, hwy = P.hwy;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    unsigned int vmask = 0;                       // validity of the lane's pixels: column 8hh+k < winW, row r < winH
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (8 * hh + k < winW && r < winH) vmask |= 1u << k;
+    bool st = true;
+    float errv = 0.f;
+    const int pimg = P.prev_image0 + pair * P.prev_image_step, nimg = P.next_image0 + pair * P.next_image_step;
+
+    for (int level = P.nlev - 1; level >= 0; --level) {
+        const LKLevel& L = P.lv[level];
+        const int w = L.w, h = L.h, ipitch = L.ipitch, jpitch = L.jpitch;
+        const uint8_t* __restrict__ I = L.I + (size_t)pimg * L.istride;
+        const uint8_t* __restrict__ J = L.J + (size_t)nimg * L.jstride;
+        const int ilow = ((((unsigned long long)I) & 3ull) == 0 && (ipitch & 3) == 0) ? 0 : 4;   // see load12
+        const int jlow = ((((unsigned long long)J) & 3ull) == 0 && (jpitch & 3) == 0) ? 0 : 4;
+        const float sc = __int_as_float((127 - level) << 23);        // 2^-level
+        const float ppx = ptx * sc, ppy = pty * sc;
+        if (level == P.nlev - 1) {
+            if (P.flags & OFB_LK_USE_INITIAL_FLOW) { nx = nx * sc; ny = ny * sc; }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = nx * 2.f; ny = ny * 2.f; }
+        const float px = ppx - hwx, py = ppy - hwy;
+        const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+        if (ix < -winW || ix >= w || iy < -winH || iy >= h) {
+            if (level == 0) { st = false; errv = 0.f; }
+            continue;
+        }
+        float a = px - (float)ix, b = py - (float)iy;
+        int w00, w01, w10, w11;
+        bil_weights(a, b, w00, w01, w10, w11);
+        // ---- template ---------------------------------------------------------------------------------
+        // rows iy+r-1 (A), iy+r (B), iy+r+1 (C); byte j of a row segment <-> column ix + 8hh - 1 + j, j = 0..11
+        const bool icol = ix - 1 >= ilow && ix + 8 + 15 <= w, irow = iy - 1 >= 0 && iy + 16 < h;
+        const bool ifast = icol && irow;
+        const int X0 = ix - 1 + 8 * hh;
+        unsigned int A0, A1, A2, B0, B1, B2, C0, C1, C2;
+        {
+            int ya = iy + r - 1, yb = iy + r, yc = iy + r + 1;
+            if (!irow) { ya = refl101(ya, h); yb = refl101(yb, h); yc = refl101(yc, h); }
+            load12(I, w, ipitch, X0, ya, icol, A0, A1, A2);
+            load12(I, w, ipitch, X0, yb, icol, B0, B1, B2);
+            load12(I, w, ipitch, X0, yc, icol, C0, C1, C2);
+        }
+        // Scharr, two columns per word. pa/pb/pc[i] = columns (2i, 2i+1) of rows A/B/C as 16-bit halves.
+        //   t0 = 3 (A + C) + 10 B            <= 4080                      (vertical smoothing, for gx)
+        //   t1 = C - A + 256                 in [1, 511]                  (vertical difference, for gy)
+        //   gx[k] + 4096 = t0[k+2] - t0[k] + 4096,   gy[k] + 4096 = 3 (t1[k] + t1[k+2]) + 10 t1[k+1]
+        unsigned int GX[5], GY[5];                   // (g[2i], g[2i+1]) + 4096 per half, Scharr at column ix + 8hh + k
+        {
+            unsigned int t0[6], t1[6];
+            const unsigned int aw[3] = {A0, A1, A2}, bw[3] = {B0, B1, B2}, cw[3] = {C0, C1, C2};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const unsigned int sel = (i & 1) ? 0x4342u : 0x4140u;
+                const unsigned int pa = prmt(aw[i >> 1], 0u, sel), pb = prmt(bw[i >> 1], 0u, sel), pc = prmt(cw[i >> 1], 0u, sel);
+                t0[i] = 3u * (pa + pc) + 10u * pb;
+                t1[i] = pc + 0x01000100u - pa;
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                GX[i] = t0[i + 1] + 0x10001000u - t0[i];
+                const unsigned int mid = prmt(t1[i], t1[i + 1], 0x5432u);            // (t1[2i+1], t1[2i+2])
+                GY[i] = 3u * (t1[i] + t1[i + 1]) + 10u * mid;
+            }
+        }
+        if (!ifast) {       // OpenCV's derivative images are ZERO outside the image (a zero gradient is 4096 here)
+            const bool rowin = (unsigned)(iy + r) < (unsigned)h;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const bool okl = rowin && (unsigned)(ix + 8 * hh + 2 * i) < (unsigned)w;
+                const bool okh = rowin && (unsigned)(ix + 8 * hh + 2 * i + 1) < (unsigned)w;
+                const unsigned int keep = (okl ? 0x0000ffffu : 0u) | (okh ? 0xffff0000u : 0u);
+                const unsigned int zero = (okl ? 0u : 0x00001000u) | (okh ? 0u : 0x10000000u);
+                GX[i] = (GX[i] & keep) | zero; GY[i] = (GY[i] & keep) | zero;
+            }
+        }
+        int Cp[8], Gx[8], Gy[8];
+        int iA11 = 0, iA12 = 0, iA22 = 0;
+        {
+            // biased gradients of rows r (own) and r+1 (lane + 2), one value per column k = 0..8
+            int gxa[9], gya[9], gxb[9], gyb[9];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const unsigned int nxp = __shfl_down_sync(0xffffffffu, GX[i], 2), nyp = __shfl_down_sync(0xffffffffu, GY[i], 2);
+                gxa[2 * i] = (int)(GX[i] & 0xffffu); gya[2 * i] = (int)(GY[i] & 0xffffu);
+                gxb[2 * i] = (int)(nxp & 0xffffu); gyb[2 * i] = (int)(nyp & 0xffffu);
+                if (i < 4) {
+                    gxa[2 * i + 1] = (int)(GX[i] >> 16); gya[2 * i + 1] = (int)(GY[i] >> 16);
+                    gxb[2 * i + 1] = (int)(nxp >> 16); gyb[2 * i + 1] = (int)(nyp >> 16);
+                }
+            }
+            // template value: rows B, C from column ix + 8hh on = byte 1 of the segments; the same dp2a taps as the
+            // Newton loop (pixel k reads bytes k, k+1 of both rows)
+            const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+            const unsigned int tt[4] = {__funnelshift_r(B0, B1, 8), __funnelshift_r(B0, B1, 16), __funnelshift_r(B1, B2, 8), __funnelshift_r(B1, B2, 16)};
+            const unsigned int uu[4] = {__funnelshift_r(C0, C1, 8), __funnelshift_r(C0, C1, 16), __funnelshift_r(C1, C2, 8), __funnelshift_r(C1, C2, 16)};
+            const int c0 = (1 << 13) - (4096 << 14);          // rounding constant minus the bias times the weight sum 2^14
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int s_ = ((k >> 2) << 1) | (k & 1);
+                int iv;
+                if ((k & 2) == 0) { iv = dp2a_lo(Wt, tt[s_], 1 << 8); iv = dp2a_lo(Wb, uu[s_], iv); }
+                else { iv = dp2a_hi(Wt, tt[s_], 1 << 8); iv = dp2a_hi(Wb, uu[s_], iv); }
+                iv >>= 9;
+                int gx = (gxa[k] * w00 + gxa[k + 1] * w01 + gxb[k] * w10 + gxb[k + 1] * w11 + c0) >> 14;
+                int gy = (gya[k] * w00 + gya[k + 1] * w01 + gyb[k] * w10 + gyb[k + 1] * w11 + c0) >> 14;
+                if (!((vmask >> k) & 1u)) { gx = 0; gy = 0; }
+                Cp[k] = 256 - 512 * iv; Gx[k] = gx; Gy[k] = gy;
+                iA11 += gx * gx; iA12 += gx * gy; iA22 += gy * gy;
+            }
+        }
+        const float A11 = warp_sum_exact_f(iA11) * FLT_SCALE;
+        const float A12 = warp_sum_exact_f(iA12) * FLT_SCALE;
+        const float A22 = warp_sum_exact_f(iA22) * FLT_SCALE;
+        float D2 = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = A11 - A22;
+        const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)))) /
+                             (float)(2 * winW * winH);
+        if ((double)minEig < P.min_eig_thr || D2 < 1.1920928955078125e-7f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D2 = 1.f / D2;
+        float qx = nx - hwx, qy = ny - hwy;
+        float pdx = 0.f, pdy = 0.f;
+        bool lost = false;
+        unsigned int T0 = 0, T1 = 0, T2 = 0, U0 = 0, U1 = 0, U2 = 0;
+        int cjx = INT_MIN, cjy = INT_MIN;
+        for (int j = 0; j < P.max_count; ++j) {
+            const int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { lost = true; break; }
+            a = qx - (float)jx; b = qy - (float)jy;
+            bil_weights(a, b, w00, w01, w10, w11);
+            const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+            if (jx != cjx || jy != cjy) {               // the patch rows stay in registers while the integer position holds
+                const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
+                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
+                U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                cjx = jx; cjy = jy;
+            }
+            int ib1 = 0, ib2 = 0;
+            LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
+                ib1 += diff * Gx[k]; ib2 += diff * Gy[k];
+            })
+            const float b1 = warp_sum_exact_f(ib1) * FLT_SCALE;
+            const float b2 = warp_sum_exact_f(ib2) * FLT_SCALE;
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D2);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D2);
+            qx += dx; qy += dy;
+            nx = qx + hwx; ny = qy + hwy;
+            // delta.ddot(delta) <= eps^2, evaluated in double by OpenCV: fp32 decides unless it is within 1e-6 of the bound
+            const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            bool conv = s2 < P.eps_lo;
+            if (!conv && !(s2 > P.eps_hi)) conv = (double)dx * (double)dx + (double)dy * (double)dy <= P.eps;
+            if (conv) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (lost && level == 0) st = false;
+        if (st && level == 0) {
+            const float rx = nx - hwx, ry = ny - hwy;
+            const int jx = __float2int_rd(rx), jy = __float2int_rd(ry);
+            if (jx < -winW || jx >= w || jy < -winH || jy >= h) { st = false; }
+            else {
+                a = rx - (float)jx; b = ry - (float)jy;
+                bil_weights(a, b, w00, w01, w10, w11);
+                const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
+                if (jx != cjx || jy != cjy) {
+                    const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
+                    load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                    U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
+                    U2 = __shfl_down_sync(0xffffffffu, T2, 2);
+                }
+                int ie = 0;
+                LKF_FOR_PIXELS(T0, T1, T2, U0, U1, U2, Wt, Wb, {
+                    if ((vmask >> k) & 1u) ie += abs(diff);
+                })
+                errv = (float)__reduce_add_sync(0xffffffffu, ie) * (1.f / (float)(32 * winW * winH));
+            }
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
+        status[po] = st ? 1 : 0;
+        if (err) err[po] = st ? errv : 0.f;
+    }
+}
+
 }  // namespace
 
 size_t ofb_lk_warp_smem(int win_w, int win_h)
@@ -530,10 +755,19 @@ int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_s
     P.nlev = eff;
     fill_levels(&P.prev, prev);
     fill_levels(&P.next, next);
+    for (int l = 0; l < eff; ++l) {
+        LKLevel& L = P.lv[l];
+        L.I = P.prev.base[l]; L.J = P.next.base[l]; L.istride = P.prev.stride[l]; L.jstride = P.next.stride[l];
+        L.w = P.prev.w[l]; L.h = P.prev.h[l]; L.ipitch = P.prev.pitch[l]; L.jpitch = P.next.pitch[l];
+    }
     P.win_w = win_w; P.win_h = win_h;
+    P.hwx = (win_w - 1) * 0.5f; P.hwy = (win_h - 1) * 0.5f;
     P.max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     double e = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
     P.eps = e * e;
+    P.eps_lo = (float)(P.eps * (1.0 - 1e-6)); P.eps_hi = (float)(P.eps * (1.0 + 1e-6));
+    if (!((double)P.eps_lo < P.eps)) P.eps_lo = 0.f;                 // (eps^2 too small for the bracket: always ask fp64)
+    if (!((double)P.eps_hi > P.eps)) P.eps_hi = INFINITY;
     P.min_eig_thr = min_eig_thr;
     P.flags = flags;
     P.prev_image0 = prev_image0; P.prev_image_step = prev_step;
@@ -542,8 +776,13 @@ int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_s
     const char* env = getenv("OFB_LK_GENERIC");      // parity tests cross-check the two kernels
     if (win_w <= 16 && win_h <= 15 && !(env && env[0] == '1')) {
         dim3 fgrid(ofb_div_up(n_uniform, LKF_WARPS), n_pairs);
-        lk_track_fast_kernel<<<fgrid, LKF_WARPS * 32, 0, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts,
-                                                                       counts_stride, n_uniform, pts_stride);
+        const char* v1 = getenv("OFB_LK_V1");            // first-generation register-resident kernel (cross-check / A-B timing)
+        if (v1 && v1[0] == '1')
+            lk_track_fast_kernel<<<fgrid, LKF_WARPS * 32, 0, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts,
+                                                                           counts_stride, n_uniform, pts_stride);
+        else
+            lk_track_fast2_kernel<<<fgrid, LKF_WARPS * 32, 0, ctx->stream>>>(P, prev_pts, next_pts, status, err, counts,
+                                                                            counts_stride, n_uniform, pts_stride);
         OFB_LAUNCH_CHECK(ctx);
         return OFB_OK;
     }

@@ -8,12 +8,22 @@ struct LKLevelSet {
     int w[OFB_MAX_LEVELS], h[OFB_MAX_LEVELS], pitch[OFB_MAX_LEVELS];
 };
 
+// one pyramid level of both images, packed so that the register-resident kernel fetches it with three 16-byte loads
+struct LKLevel {
+    const uint8_t* I; const uint8_t* J;          // image 0 of the batch at this level
+    unsigned long long istride, jstride;         // bytes between images of the batch
+    int w, h, ipitch, jpitch;
+};
+
 struct LKParams {
     LKLevelSet prev, next;
+    LKLevel lv[OFB_MAX_LEVELS];
     int nlev;                     // levels actually used (after OpenCV's window-size cut)
     int win_w, win_h, max_count, flags;
     double eps;                   // squared, clamped
     double min_eig_thr;
+    float eps_lo, eps_hi;         // fp32 brackets of eps: |delta|^2 below eps_lo / above eps_hi decides without fp64
+    float hwx, hwy;               // (win - 1) / 2
     int prev_image0, prev_image_step, next_image0, next_image_step;   // image of pair p = image0 + p*step
 };
 

@@ -325,6 +325,12 @@ def test_two_kernel_variants_agree(ctx):
         for win in ((15, 15), (9, 13), (16, 15)):
             kw = dict(winSize=win, maxLevel=3, criteria=(3, 20, 0.03))
             n1, s1, e1 = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, ctx=ctx, **kw)
+            os.environ["OFB_LK_V1"] = "1"           # first-generation register-resident kernel: same integers, same bits
+            try:
+                n0, s0, e0 = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, ctx=ctx, **kw)
+            finally:
+                os.environ["OFB_LK_V1"] = "0"
+            assert np.array_equal(s1, s0) and np.array_equal(n1, n0) and np.array_equal(e1, e0), (case, win)
             os.environ["OFB_LK_GENERIC"] = "1"
             try:
                 n2, s2, e2 = ofb200.calcOpticalFlowPyrLK(a, b, pts, None, ctx=ctx, **kw)
