@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement (BASELINE.json): 1080p frame-pairs/s (detect + LK flow + velocity
-solve) and Monte-Carlo trials/s.
+"""bench.py -- headline measurement (BASELINE.json): 1080p frame-pairs/s (detect + LK flow + velocity solve) and
+Monte-Carlo trials/s, plus the other three BASELINE configurations, all in the ONE JSON line of the default run.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path (pyramids -> Shi-Tomasi -> pyramidal LK -> velocity solve) over one
-batch of `--batch` independent synthetic 1080p frame pairs (BASELINE config 2: 1000 features, maxLevel 4).
+A "step" is one pass of the hot path (pyramids -> Shi-Tomasi -> pyramidal LK -> velocity solve) over one batch of
+`--batch` consecutive synthetic 1080p frame pairs of one stream (BASELINE config 2: 1000 features, maxLevel 4).
   value      pairs/s with the frames already resident in HBM, CUDA events on the library's stream
-  e2e        the same through the public Python API with pinned HOST frames: H2D of both frames and D2H
-             of the results inside the timed region
-  roofline   the dominant kernel: algorithmic bytes per launch / its CUDA-event duration, vs the measured
-             HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  cv2 4.13 goodFeaturesToTrack + calcOpticalFlowPyrLK (the reference's own un-vendored
-             dependency) + the oracle port of the reference's Python solve_lgs, on the host cores
-  mc         Monte-Carlo error sweep (config 3): 1e8 trials x 50 points, trial ranges sharded over ranks
-With N>1 every rank processes its own batch (streams shard with no data-path collective): weak scaling.
+  e2e        the same through the public Python API with pinned HOST frames: H2D of the frames and D2H of the results
+             inside the timed region
+  roofline   the dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured HBM copy
+             bandwidth (MEASURED_PEAKS.json); `issue` = the same kernel against the warp-issue peak that actually bounds it
+  cpu_baseline  cv2 4.13 goodFeaturesToTrack + calcOpticalFlowPyrLK (the reference's own un-vendored dependency) + the
+             oracle port of the reference's Python solve_lgs, on the host cores
+  mc         config 3: Monte-Carlo error sweep, 1e8 trials x 50 points, trial ranges sharded over the ranks, the merge
+             all-reduce inside the timed region; fp32 and fp64 figures; CPU baseline = the oracle port of of_simulation
+  c1 / c4    configs 1 and 4: 640x480 / 3840x2160 single-pair latency (p50), each with its CPU baseline
+  c5         config 5: 256-stream 1280x720 fleet, stream-sharded over the ranks: pair path, device-resident lifecycle,
+             lifecycle end to end from host frames; CPU baseline = one process per core over the streams
+With N>1 every rank processes its own C2 batch (streams shard with no data-path collective): weak scaling; the C5
+fleet and the Monte-Carlo job have a fixed total size: strong scaling.
 """
 import argparse
 import json
@@ -38,6 +43,19 @@ METRIC = "1080p frame-pairs/s (LK flow+velocity solve)"
 MC_TOTAL, MC_POINTS = 100_000_000, 50
 MC_AXES = ("flow_errors", "distance_error", "ang_vel_error", "normal_error", "translation_error", "orientation",
            "height", "point_position")
+GEOM = {"c1": (640, 480, 200, 3), "c2": (W, H, K_FEAT, MAX_LEVEL), "c4": (3840, 2160, 5000, 5), "c5": (1280, 720, 500, 3)}
+FLEET = 256
+SOLVE_NOTE = ("solve_lgs = oracle port of the reference's Python loop with pre-allocated A, B (the reference grows them "
+              "with np.append, ~4x slower at 1000 points: this baseline is faster than the verbatim reference)")
+
+
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (stdout carries only the JSON line)"""
+    sys.stderr.write("[bench %6.1fs] %s\n" % (time.time() - _T0, msg))
+    sys.stderr.flush()
 
 
 def parse():
@@ -51,28 +69,49 @@ def parse():
     ap.add_argument("--mc-trials", type=int, default=MC_TOTAL)
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C4 / C5 legs (kernel A-B runs)")
     ap.add_argument("--ref-pairs", type=int, default=16, help="pairs per step of the reference arm")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"],
-                    help="c2 (default, the headline line); c1 = 640x480 and c4 = 3840x2160 single-pair latency; c5 = 256-stream 720p fleet")
+    ap.add_argument("--cpu-job", default=None, choices=["fleet", "mc"],
+                    help="internal: run one multi-process CPU baseline in this (CUDA-free) process and print its JSON")
+    ap.add_argument("--workload", default="all", choices=["all", "c1", "c2", "c4", "c5"],
+                    help="all (default: every BASELINE configuration in one line) or a single configuration")
     return ap.parse_args()
 
 
 def bind_near_gpu(index):
     """Multi-GPU hosts: run this rank (and first-touch its pinned frame buffers) on the CPUs NVML reports as closest to
-    its GPU, so that the end-to-end copies do not cross the socket interconnect. Best effort: ignored where the
-    container's cpuset does not allow it."""
+    its GPU, so that the end-to-end copies do not cross the socket interconnect. Returns what happened (it goes into
+    the JSON line: whether the affinity was applied decides how the 8-GPU end-to-end number is read)."""
+    info = {"applied": False}
     try:
+        before = sorted(os.sched_getaffinity(0))
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        after = sorted(os.sched_getaffinity(0))
+        info.update(applied=True, cpus_before=len(before), cpus_after=len(after), first_cpu=after[0], last_cpu=after[-1])
+    except Exception as e:
+        info["error"] = repr(e)[:120]
+    return info
+
+
+def numa_node_of(arr):
+    """NUMA node of the first page of a (pinned) host array via move_pages(2) with a NULL node list; None when the call
+    is not available in this container."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        page = ctypes.c_void_p(arr.ctypes.data & ~4095)
+        status = ctypes.c_int(-1)
+        rc = libc.syscall(279, 0, ctypes.c_ulong(1), ctypes.byref(page), None, ctypes.byref(status), 0)   # __NR_move_pages
+        return int(status.value) if rc == 0 and status.value >= 0 else None
     except Exception:
-        pass
+        return None
 
 
-def make_data(distinct, rank):
+def make_data(distinct, rank, w=W, h=H, base=100):
     import synth
-    pairs = [synth.make_pair(H, W, stream_id=rank, pair_id=100 * rank + i) for i in range(distinct)]
-    return pairs
+    return [synth.make_pair(h, w, stream_id=rank, pair_id=base * rank + i) for i in range(distinct)]
 
 
 def imu_array(ofb200, pairs, batch):
@@ -161,27 +200,34 @@ def stream_pair(pairs, k):
     return b, a, back
 
 
-def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
-    """The reference's CPU path on identical frames: cv2 gftt + LK + Python solve_lgs (oracle port)."""
+# ---- the reference's CPU path ---------------------------------------------------------------------------------
+def cpu_one_pair(a, b, mo, feat, ml):
+    """cv2 goodFeaturesToTrack + calcOpticalFlowPyrLK + the Python solve_lgs on one pair -> (velocity, split seconds, pts)"""
     import cv2
     from oracle import velocity_oracle as vo
+    t1 = time.perf_counter()
+    p = cv2.goodFeaturesToTrack(a, feat, QUALITY, MIN_DIST, blockSize=BLOCK)
+    t2 = time.perf_counter()
+    nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=WIN, maxLevel=ml, criteria=CRIT)
+    t3 = time.perf_counter()
+    ok = st.ravel() == 1
+    newp = nxt.reshape(-1, 2)[ok]
+    x = (newp.astype(np.float64) - np.array([mo["cx"], mo["cy"]])) / mo["f"]
+    u = (newp - p.reshape(-1, 2)[ok]).astype(np.float64) / (mo["f"] * mo["dt"])
+    v = vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], variant="node")[0]
+    t4 = time.perf_counter()
+    return v, (t2 - t1, t3 - t2, t4 - t3), p
+
+
+def cpu_pair_path(get_pair, feat, ml, seconds, threads, max_pairs=None):
+    """The reference's CPU path, pairs one after the other (as its loops run them), cv2 with `threads` threads."""
+    import cv2
     cv2.setNumThreads(threads)
-    done, t0 = 0, time.perf_counter()
-    split = np.zeros(3)
+    done, t0, split = 0, time.perf_counter(), np.zeros(3)
     while True:
-        a, b, mo = stream_pair(pairs, done)
-        t1 = time.perf_counter()
-        p = cv2.goodFeaturesToTrack(a, K_FEAT, QUALITY, MIN_DIST, blockSize=BLOCK)
-        t2 = time.perf_counter()
-        nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=WIN, maxLevel=MAX_LEVEL, criteria=CRIT)
-        t3 = time.perf_counter()
-        ok = st.ravel() == 1
-        newp = nxt.reshape(-1, 2)[ok]
-        x = (newp.astype(np.float64) - np.array([mo["cx"], mo["cy"]])) / mo["f"]
-        u = (newp - p.reshape(-1, 2)[ok]).astype(np.float64) / (mo["f"] * mo["dt"])
-        vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], variant="node")
-        t4 = time.perf_counter()
-        split += [t2 - t1, t3 - t2, t4 - t3]
+        a, b, mo = get_pair(done)
+        _, sp, _ = cpu_one_pair(a, b, mo, feat, ml)
+        split += sp
         done += 1
         el = time.perf_counter() - t0
         if (max_pairs and done >= max_pairs) or (not max_pairs and el >= seconds and done >= 3):
@@ -189,31 +235,95 @@ def cpu_pair_path(pairs, seconds, threads, max_pairs=None):
     return done / el, done, (split / done * 1e3).tolist()
 
 
-def cpu_pair_path_generic(pairs, w, h, feat, ml, seconds):
-    """cv2 + oracle solve on pairs of another geometry (C1 / C4 latency lines)."""
+_FLEET_PAIRS = None
+
+
+def _fleet_worker(idx):
     import cv2
-    from oracle import velocity_oracle as vo
-    cv2.setNumThreads(len(os.sched_getaffinity(0)))
-    done, t0, split = 0, time.perf_counter(), np.zeros(3)
-    while True:
-        a, b, mo = pairs[done % len(pairs)]
-        t1 = time.perf_counter()
-        p = cv2.goodFeaturesToTrack(a, feat, QUALITY, MIN_DIST, blockSize=BLOCK)
-        t2 = time.perf_counter()
-        nxt, st, err = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=WIN, maxLevel=ml, criteria=CRIT)
-        t3 = time.perf_counter()
-        ok = st.ravel() == 1
-        newp = nxt.reshape(-1, 2)[ok]
-        x = (newp.astype(np.float64) - np.array([mo["cx"], mo["cy"]])) / mo["f"]
-        u = (newp - p.reshape(-1, 2)[ok]).astype(np.float64) / (mo["f"] * mo["dt"])
-        vo.solve_lgs(x, u, mo["d"], mo["n"], mo["w"], variant="node")
-        t4 = time.perf_counter()
-        split += [t2 - t1, t3 - t2, t4 - t3]
-        done += 1
+    cv2.setNumThreads(1)
+    a, b, mo = _FLEET_PAIRS[idx % len(_FLEET_PAIRS)]
+    w, h, feat, ml = GEOM["c5"]
+    cpu_one_pair(a, b, mo, feat, ml)
+    return 1
+
+
+def cpu_fleet(pairs, ncores, streams=FLEET):
+    """the C5 CPU baseline is one process per core over the 256 streams (cv2 single-threaded in each)."""
+    global _FLEET_PAIRS
+    import multiprocessing as mp
+    _FLEET_PAIRS = pairs
+    with mp.get_context("fork").Pool(ncores) as pool:
+        pool.map(_fleet_worker, range(ncores))                 # start the workers, import cv2, touch the frames
+        t0 = time.perf_counter()
+        n = sum(pool.map(_fleet_worker, range(streams), chunksize=max(1, streams // (4 * ncores))))
         el = time.perf_counter() - t0
-        if el >= seconds and done >= 3:
-            break
-    return done / el, done, (split / done * 1e3).tolist()
+    return n / el, n
+
+
+_MC_ARGS = None
+
+
+def _mc_worker(job):
+    from oracle import velocity_oracle as vo
+    seed, iters = job
+    pos, tf = _MC_ARGS
+    rng = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    vo.of_simulation(iters, rng, np.ones(3), np.ones(3), 1.0, np.array([0.0, 0, 1]), np.array([0.02, 0, 0.205]), pos, tf,
+                     0.00071, 0.005, 0.01, 0.056 * np.sqrt(2) * 1.23, 0.056 * 1.23, 0.00065)
+    return iters, time.perf_counter() - t0
+
+
+def cpu_mc(ncores, total):
+    """of_simulation (oracle port of simulation.py:36-66, same arithmetic per trial) on 1 core for >= 200
+    trials and on all cores via multiprocessing (independent seeds), extrapolated linearly to the job size."""
+    global _MC_ARGS
+    import multiprocessing as mp
+    from oracle import velocity_oracle as vo
+    pts = np.load(os.path.join(ROOT, "tests", "golden", "points.npy"))
+    d = np.array(pts, dtype=np.float64)
+    d[:, 0] = (d[:, 0] - d[:, 0].mean()) * 1.27; d[:, 1] = (d[:, 1] - d[:, 1].mean()) * 0.93
+    pos = d[:MC_POINTS]
+    tf = vo.generate_test_data(pos, np.ones(3), np.ones(3), 1.0, [0, 0, 1], [0.02, 0, 0.205])
+    _MC_ARGS = (pos, tf)
+    n1, t1 = _mc_worker((1, 200))
+    with mp.get_context("fork").Pool(ncores) as pool:
+        pool.map(_mc_worker, [(100 + i, 2) for i in range(ncores)])
+        t0 = time.perf_counter()
+        res = pool.map(_mc_worker, [(200 + i, 100) for i in range(ncores)])
+        el = time.perf_counter() - t0
+    nall = sum(r[0] for r in res)
+    one, allc = n1 / t1, nall / el
+    return {"value": allc, "unit": "trials/s", "cores": ncores, "kind": "port", "value_1core": one,
+            "sample": "oracle port of of_simulation (simulation.py:36-66, NumPy, %d points): %d trials on 1 core, %d trials on %d "
+                      "cores (multiprocessing, independent seeds)" % (MC_POINTS, n1, nall, ncores),
+            "extrapolated_seconds_for_job": {"trials": total, "one_core": total / one, "all_cores": total / allc,
+                                             "note": "linear extrapolation, not run"}}
+
+
+def cpu_job_subprocess(name, total=0, timeout=240):
+    """The multi-process CPU baselines fork worker pools; forking THIS process (CUDA context, NCCL and NVML threads) is
+    not safe, so they run in a fresh interpreter that never touches the GPU and report back through stdout."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-job", name, "--mc-trials", str(int(total))]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("cpu job %s failed: %s" % (name, out.stderr[-300:]))
+    return json.loads(out.stdout.strip().split("\n")[-1])
+
+
+def cpu_job_main(args):
+    ncores = len(os.sched_getaffinity(0))
+    if args.cpu_job == "fleet":
+        w, h, feat, ml = GEOM["c5"]
+        pairs = make_data(8, 0, w, h, base=1000)
+        v, n = cpu_fleet(pairs, ncores)
+        print(json.dumps({"value": v, "unit": "pairs/s", "cores": ncores, "kind": "port",
+                          "sample": "%d streams, one pair each, one process per core (cv2 single-threaded per process); %s" % (n, SOLVE_NOTE)}))
+    else:
+        print(json.dumps(cpu_mc(ncores, args.mc_trials)))
 
 
 def reference_arm(args):
@@ -223,27 +333,29 @@ def reference_arm(args):
         return
     ncores = len(os.sched_getaffinity(0))
     pairs = make_data(min(args.distinct, 4), 0)
+    get = lambda k: stream_pair(pairs, k)
     for _ in range(args.warmup):
-        cpu_pair_path(pairs, 0, ncores, max_pairs=1)
+        cpu_pair_path(get, K_FEAT, MAX_LEVEL, 0, ncores, max_pairs=1)
     t0 = time.perf_counter()
     tot = 0
     for _ in range(args.steps):
-        _, n, split = cpu_pair_path(pairs, 0, ncores, max_pairs=args.ref_pairs)
+        _, n, split = cpu_pair_path(get, K_FEAT, MAX_LEVEL, 0, ncores, max_pairs=args.ref_pairs)
         tot += n
     el = time.perf_counter() - t0
     val = tot / el
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": args.ref_pairs},
+            "config": {"workload": WORKLOAD, "pairs_per_step": args.ref_pairs,
+                       "note": "the CPU arm runs its pairs one after the other, so its rate does not depend on the pairs per step"},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": ncores, "kind": "port",
-                             "sample": "%d pairs: cv2 4.13 goodFeaturesToTrack+calcOpticalFlowPyrLK + oracle port of the "
-                                       "reference's Python solve_lgs, all host threads; ms gftt/LK/solve = %s" %
-                                       (tot, [round(s, 1) for s in split])},
+                             "sample": "%d pairs: cv2 4.13 goodFeaturesToTrack+calcOpticalFlowPyrLK, all host threads; ms "
+                                       "gftt/LK/solve = %s; %s" % (tot, [round(s, 1) for s in split], SOLVE_NOTE)},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ---- Monte-Carlo (config 3) -----------------------------------------------------------------------------------
 def mc_workload(ofb200, trials_total):
     sim = ofb200.simulation
     pts = np.load(os.path.join(ROOT, "tests", "golden", "points.npy"))[:MC_POINTS]
@@ -258,31 +370,153 @@ def mc_workload(ofb200, trials_total):
     return steps, np.vstack(pos), np.vstack(flow), per_step
 
 
-def extra_workload(args):
-    """BASELINE configs 4 and 5 (not the headline line): C4 = 3840x2160, 5000 features, maxLevel 5, per-pair p50
-    latency of one resident pair; C5 = 256 concurrent 1280x720 streams, 500 features, maxLevel 3, streams
-    sharded over the ranks, aggregate pairs/s. One JSON line each."""
+def leg_mc(args, ofb200, torch, dist, rank, world, local):
+    """1e8 trials x 50 points over 800 sweep steps; this rank's trial range; per-step sums stay on the device and are
+    merged by ONE all-reduce (8 doubles per step) on the same stream, inside the timed region (CUDA events)."""
+    sim = ofb200.simulation
+    steps, pos, flow, per_step = mc_workload(ofb200, args.mc_trials)
+    begin, count = sim.shard_range(per_step, rank, world)
+    arr = sim._steps_array(steps)
+    s = torch.cuda.current_stream()
+    mctx = ofb200.Context(local, stream=s.cuda_stream)          # the library works on torch's stream: one timeline
+    d_pos, d_flow = torch.from_numpy(pos).cuda(), torch.from_numpy(flow).cuda()
+    d_sums = torch.zeros((len(steps), 8), dtype=torch.float64, device="cuda")
+
+    def job(precision, want_R=True):
+        if count > 0:
+            sim.run_steps(arr, d_pos, d_flow, count, seed=1, trial_begin=begin, precision=precision, ctx=mctx, want_R=want_R,
+                          sums_out=d_sums)
+        else:
+            d_sums.zero_()
+        if dist is not None:
+            dist.all_reduce(d_sums, op=dist.ReduceOp.SUM)
+
+    def timed(precision, want_R=True, reps=3):
+        out = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s); job(precision, want_R); e1.record(s)
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        ms = float(np.median(out))
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms, out
+
+    for _ in range(2):                       # warm-up at full size (clocks drop while the step descriptors are built)
+        job("fp32")
+    ms32, reps32 = timed("fp32")
+    sums = d_sums.cpu().numpy().reshape(-1).view(ofb200._lib.MCSUMS_DTYPE).copy()
+    ms32_nr, _ = timed("fp32", want_R=False)
+    ms64, _ = timed("fp64", reps=2)
+    mean, std, mR, n = sim.stats_from_sums(sums, steps)
+    total = float(n.sum())
+    flop = 140 * MC_POINTS + 300
+    mctx.close()
+    return {"metric": "MC trials/s", "value": total / (ms32 * 1e-3), "unit": "trials/s", "trials": total, "points": MC_POINTS,
+            "steps": len(steps), "axes": list(MC_AXES), "ms": ms32, "ms_reps": [round(r, 3) for r in reps32],
+            "value_fp64": total / (ms64 * 1e-3), "ms_fp64": ms64, "value_without_R": total / (ms32_nr * 1e-3),
+            "scaling": "strong", "dtype": "f32 per-point arithmetic with f64 solve/statistics (`value`); f64 throughout (`value_fp64`, "
+                                          "what the reference computes in)",
+            "timed_region": "per-step sums left on the device + one all-reduce(sum) of %d x 8 doubles on the same stream, CUDA "
+                            "events, max over ranks" % len(steps),
+            "fp32_tflops_alg": total * flop / (ms32 * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
+            "check_mean_v_step0": [round(float(x), 4) for x in mean[0]]}
+
+
+# ---- single-pair latency (configs 1 and 4) --------------------------------------------------------------------
+def leg_latency(args, ofb200, torch, ctx, name, rank):
     import ctypes as C
-    import torch
-    import ofb200
-    import synth
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    ctx = ofb200.Context(local)
-    if args.workload == "c4":
-        w, h, feat, ml, B, distinct = 3840, 2160, 5000, 5, 1, 2
-    elif args.workload == "c1":
-        w, h, feat, ml, B, distinct = 640, 480, 200, 3, 1, 2
-    else:
-        w, h, feat, ml, distinct = 1280, 720, 500, 3, 8
-        B = 256 // world + (1 if rank < 256 % world else 0)
-    pairs = [synth.make_pair(h, w, stream_id=rank, pair_id=1000 * rank + i) for i in range(distinct)]
+    w, h, feat, ml = GEOM[name]
+    pairs = make_data(2, rank, w, h, base=1000)
+    mo0 = pairs[0][2]
+    cfg = ofb200.make_pair_cfg(w, h, feat, QUALITY, MIN_DIST, BLOCK, WIN, ml, CRIT, variant="node",
+                               principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"], flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
+    imu = imu_array(ofb200, pairs, 1)
+    a = torch.from_numpy(pairs[0][0][None]).cuda(); b = torch.from_numpy(pairs[0][1][None]).cuda()
+    d_imu = torch.from_numpy(imu.view(np.uint8).reshape(-1).copy()).cuda()
+    d_res = torch.zeros(ofb200._lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    P = ofb200._lib.ptr
+
+    def step():
+        ofb200._lib.check(ctx.lib.ofb_frame_pairs(ctx.h, C.byref(cfg), 1, P(a), P(b), w, w * h, P(d_imu), None, None, P(d_res),
+                                                  None, None, None))
+    for _ in range(max(args.warmup, 5)):
+        step()
+    ctx.sync()
+    lat = []
+    for _ in range(max(args.steps, 50)):
+        ctx.timer_start(); step(); lat.append(ctx.timer_stop())
+    res = np.zeros(1, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
+    ctx.set_profile(True)
+    for _ in range(3):
+        step()
+    ctx.set_profile(True)
+    for _ in range(10):
+        step()
+    sms, calls = ctx.stage_times()
+    ctx.set_profile(False)
+    # the same pair from (pageable) host arrays through the public call, result read back: what a ROS callback sees
+    ha, hb = pairs[0][0], pairs[0][1]
+    for _ in range(5):
+        ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx)
+    e2e_lat = []
+    for _ in range(max(args.steps, 50)):
+        t0 = time.perf_counter(); ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx); e2e_lat.append((time.perf_counter() - t0) * 1e3)
+    # the same camera through the device-resident feature lifecycle: (i) what velocity_measurment_node's image callback
+    # would run, one pageable host frame in, one result record out per call; (ii) resident frames, asynchronous calls
+    kw = dict(max_features=feat, min_features=feat // 2, feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+              lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30, variant="node",
+              principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"], flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=ctx)
+    trk = ofb200.StreamTracker(w, h, **kw)
+    for k in range(6):
+        tres = trk.step(hb if k & 1 else ha, imu[:1])
+    trk_lat = []
+    for k in range(max(args.steps, 50)):
+        t0 = time.perf_counter(); tres = trk.step(hb if k & 1 else ha, imu[:1]); trk_lat.append((time.perf_counter() - t0) * 1e3)
+    trk.close()
+    trk = ofb200.StreamTracker(w, h, borrow_frames=True, **kw)
+    d_tres = torch.zeros(ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    nrep = max(args.steps, 50)
+
+    def rstep(k):
+        ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(b if k & 1 else a), w, w * h, P(d_imu), None, P(d_tres), None, None, None, None))
+    for k in range(8):
+        rstep(k)
+    ctx.sync()
+    ctx.timer_start()
+    for k in range(nrep):
+        rstep(k)
+    res_ms = ctx.timer_stop() / nrep
+    trk.close()
+    label = {"c1": "C1: 640x480, 200 features, maxLevel 3", "c4": "C4: 3840x2160, 5000 features, maxLevel 5"}[name]
+    return {"metric": "%dx%d frame-pair latency p50 (detect+track+solve), ms" % (w, h), "value": float(np.percentile(lat, 50)),
+            "unit": "ms", "p95": float(np.percentile(lat, 95)), "higher_is_better": False, "samples": len(lat),
+            "config": {"workload": label + ", one resident pair per call (ofb_frame_pairs), CUDA events around each call"},
+            "e2e": {"value": float(np.percentile(e2e_lat, 50)), "unit": "ms", "p95": float(np.percentile(e2e_lat, 95)),
+                    "what": "ofb200.frame_pairs on pageable NumPy frames, result read back (host wall clock per call)",
+                    "h2d_bytes_per_step": 2 * w * h, "d2h_bytes_per_step": int(res.nbytes)},
+            "lifecycle_step": {"host_call_ms_p50": float(np.percentile(trk_lat, 50)), "host_call_ms_p95": float(np.percentile(trk_lat, 95)),
+                               "resident_ms_per_frame": res_ms, "n_tracked": int(tres["n_tracked"][0]),
+                               "solved": int(tres["flags"][0] & 1),
+                               "what": "StreamTracker.step: one frame in, pyramid + LK from the kept frame + filter + solve; "
+                                       "host_call = pageable NumPy frame in / record out, resident = device frames, asynchronous calls"},
+            "stage_ms_serial": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s / max(calls, 1), 4) for s in sms])),
+            "check": {"n_tracked": int(res["n_tracked"][0]), "v": [round(float(x), 5) for x in res["v"][0]],
+                      "truth": [round(float(x), 5) for x in pairs[0][2]["v"]]}}, pairs
+
+
+# ---- the 256-stream fleet (config 5) --------------------------------------------------------------------------
+def leg_fleet(args, ofb200, torch, dist, ctx, rank, world, local):
+    import ctypes as C
+    w, h, feat, ml = GEOM["c5"]
+    distinct = 8
+    B = FLEET // world + (1 if rank < FLEET % world else 0)
+    pairs = make_data(distinct, rank, w, h, base=1000)
     mo0 = pairs[0][2]
     cfg = ofb200.make_pair_cfg(w, h, feat, QUALITY, MIN_DIST, BLOCK, WIN, ml, CRIT, variant="node",
                                principal=(mo0["cx"], mo0["cy"]), pos_scale=1.0 / mo0["f"], flow_scale=1.0 / (mo0["f"] * mo0["dt"]))
@@ -294,171 +528,134 @@ def extra_workload(args):
     torch.cuda.synchronize()
     P = ofb200._lib.ptr
 
+    def maxr(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
     def step():
         ofb200._lib.check(ctx.lib.ofb_frame_pairs(ctx.h, C.byref(cfg), B, P(a), P(b), w, w * h, P(d_imu), None, None, P(d_res),
                                                   None, None, None))
     for _ in range(args.warmup):
         step()
-    ctx.sync()
-    if dist is not None:
-        dist.barrier()
-    if args.workload in ("c4", "c1"):
-        lat = []
-        for _ in range(max(args.steps, 50)):
-            ctx.timer_start(); step(); lat.append(ctx.timer_stop())
-        res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
-        lat = np.array(lat)
-        ctx.set_profile(True)
-        for _ in range(3):
-            step()
-        ctx.set_profile(True)
-        for _ in range(10):
-            step()
-        sms, calls = ctx.stage_times()
-        ctx.set_profile(False)
-        # the same pair from (pageable) host arrays through the public call, result read back: what a ROS callback sees
-        ha, hb = pairs[0][0], pairs[0][1]
-        for _ in range(5):
-            ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx)
-        e2e_lat = []
-        for _ in range(max(args.steps, 50)):
-            t0 = time.perf_counter(); ofb200.frame_pairs(ha[None], hb[None], imu[:1], cfg, ctx=ctx); e2e_lat.append((time.perf_counter() - t0) * 1e3)
-        # the same camera through the device-resident feature lifecycle (ofb200.StreamTracker.step: one pageable host
-        # frame in, one result record out per call) -- what velocity_measurment_node's image callback would run
-        trk = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2,
-                                   feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
-                                   lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
-                                   variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
-                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=ctx)
-        for k in range(6):
-            tres = trk.step(hb if k & 1 else ha, imu[:1])
-        trk_lat = []
-        for k in range(max(args.steps, 50)):
-            t0 = time.perf_counter(); tres = trk.step(hb if k & 1 else ha, imu[:1]); trk_lat.append((time.perf_counter() - t0) * 1e3)
-        trk.close()
-        lifecycle = {"host_call_ms_p50": float(np.percentile(trk_lat, 50)), "host_call_ms_p95": float(np.percentile(trk_lat, 95)),
-                     "n_tracked": int(tres["n_tracked"][0]), "solved": int(tres["flags"][0] & 1)}
-        cpu_ms = None
-        if not args.no_cpu:
-            try:
-                v, n_, split = cpu_pair_path_generic(pairs, w, h, feat, ml, 3.0)
-                cpu_ms = {"ms_per_pair": 1e3 / v, "ms_gftt_lk_solve": [round(x, 2) for x in split], "cores": len(os.sched_getaffinity(0))}
-            except Exception as e:
-                cpu_ms = {"unavailable": repr(e)}
-        name = "3840x2160" if args.workload == "c4" else "640x480"
-        line = {"metric": name + " frame-pair latency p50 (detect+track+solve)", "value": float(np.percentile(lat, 50)),
-                "e2e_host_call_ms_p50": float(np.percentile(e2e_lat, 50)), "lifecycle_step": lifecycle, "cpu_reference": cpu_ms,
-                "stage_ms_serial": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s / max(calls, 1), 4) for s in sms])),
-                "unit": "ms", "p95": float(np.percentile(lat, 95)), "n_gpus": 1, "steps": len(lat), "higher_is_better": False,
-                "config": {"workload": "C4: 3840x2160, 5000 features, maxLevel 5, one resident pair per call" if args.workload == "c4"
-                           else "C1: 640x480, 200 features, maxLevel 3, one resident pair per call"},
-                "check": {"n_tracked": int(res["n_tracked"][0]), "v": res["v"][0].tolist(), "truth": pairs[0][2]["v"].tolist()}}
-    else:
-        ctx.timer_start()
-        for _ in range(args.steps):
-            step()
-        ms = ctx.timer_stop()
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
-        # the same fleet through the device-resident feature lifecycle (ofb_tracker_step): one frame per
-        # stream and step, point sets kept on the device, masked top-up when fewer than half the features survive
-        trk = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2, n_streams=B,
-                                   feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
-                                   lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
-                                   variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
-                                   flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), borrow_frames=True, ctx=ctx)
-        d_tres = torch.zeros(B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = maxr(ctx.timer_stop())
+    res = np.zeros(B, ofb200._lib.RESULT_DTYPE); ctx.memcpy(res, d_res, res.nbytes)
+    # the same fleet through the device-resident feature lifecycle (ofb_tracker_step): one frame per stream
+    # and step, point sets kept on the device, masked top-up when fewer than half the features survive
+    kw = dict(max_features=feat, min_features=feat // 2, feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
+              lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30, variant="node",
+              principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"], flow_scaling=1.0 / (mo0["f"] * mo0["dt"]))
+    trk = ofb200.StreamTracker(w, h, n_streams=B, borrow_frames=True, ctx=ctx, **kw)
+    d_tres = torch.zeros(B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
 
-        def tstep(k):
-            ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(b if k & 1 else a), w, w * h, P(d_imu), None, P(d_tres), None, None,
-                                                       None, None))
-        for k in range(2 * max(args.warmup, 1)):
-            tstep(k)
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
-        l0 = ctx.launch_count()
-        ctx.timer_start()
-        for k in range(2 * args.steps):
-            tstep(k)
-        tms = ctx.timer_stop()
-        tl = ctx.launch_count() - l0
-        if dist is not None:
-            t = torch.tensor([tms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tms = float(t.item())
-        tres = np.zeros(B, ofb200._lib.TRACK_RESULT_DTYPE); ctx.memcpy(tres, d_tres, tres.nbytes)
-        trk.close()
-        lifecycle = {"value": 256 * 2 * args.steps / (tms * 1e-3), "unit": "pairs/s", "ms_per_step": tms / (2 * args.steps),
-                     "gpu_launches_per_step": tl / (2 * args.steps),
-                     "what": "ofb_tracker_step: new frame -> pyramid -> LK from the kept frame -> status filter -> solve -> "
-                             "(masked top-up when <= %d points survive); resident frames used in place (borrow_frames)" % (feat // 2),
-                     "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
-                               "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
-        # end to end: the fleet's frames arrive in (pinned) HOST memory every step. Four sub-fleets on four contexts
-        # (own streams): the H2D copy of one sub-fleet overlaps the kernels of the others; every step's result records
-        # are read back to the host. Bytes per step: B frames in, B result records out.
-        NSUB = 4 if B >= 8 else 1
-        bounds = [B * i // NSUB for i in range(NSUB + 1)]
-        subs = []
-        for i in range(NSUB):
-            n_i = bounds[i + 1] - bounds[i]
-            c_i = ofb200.Context(local)
-            t_i = ofb200.StreamTracker(w, h, max_features=feat, min_features=feat // 2, n_streams=n_i,
-                                       feature_params=dict(qualityLevel=QUALITY, minDistance=MIN_DIST, blockSize=BLOCK),
-                                       lk_params=dict(winSize=WIN, maxLevel=ml, criteria=CRIT), topup="node", mask_radius=30,
-                                       variant="node", principal=(mo0["cx"], mo0["cy"]), scaling=1.0 / mo0["f"],
-                                       flow_scaling=1.0 / (mo0["f"] * mo0["dt"]), ctx=c_i)
-            ha_i = torch.from_numpy(np.stack([pairs[j % distinct][0] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
-            hb_i = torch.from_numpy(np.stack([pairs[j % distinct][1] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
-            dimu_i = torch.from_numpy(imu[bounds[i]:bounds[i + 1]].view(np.uint8).reshape(-1).copy()).cuda()
-            dres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-            hres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-            subs.append((c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i))
-        torch.cuda.synchronize()
+    def tstep(k):
+        ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(b if k & 1 else a), w, w * h, P(d_imu), None, P(d_tres), None, None,
+                                                   None, None))
+    for k in range(2 * max(args.warmup, 1)):
+        tstep(k)
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for k in range(2 * args.steps):
+        tstep(k)
+    tms = maxr(ctx.timer_stop())
+    tl = ctx.launch_count() - l0
+    tres = np.zeros(B, ofb200._lib.TRACK_RESULT_DTYPE); ctx.memcpy(tres, d_tres, tres.nbytes)
+    trk.close()
+    lifecycle = {"value": FLEET * 2 * args.steps / (tms * 1e-3), "unit": "pairs/s", "ms_per_step": tms / (2 * args.steps),
+                 "gpu_launches_per_step": tl / (2 * args.steps),
+                 "what": "ofb_tracker_step: new frame -> pyramid -> LK from the kept frame -> status filter -> solve -> "
+                         "(masked top-up when <= %d points survive); resident frames used in place (borrow_frames)" % (feat // 2),
+                 "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
+                           "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
+    # end to end: the fleet's frames arrive in (pinned) HOST memory every step. Four sub-fleets on four contexts (own
+    # streams): the H2D copy of one sub-fleet overlaps the kernels of the others; every step's result records are read
+    # back to the host. Bytes per step: B frames in, B result records out.
+    NSUB = 4 if B >= 8 else 1
+    bounds = [B * i // NSUB for i in range(NSUB + 1)]
+    subs = []
+    for i in range(NSUB):
+        n_i = bounds[i + 1] - bounds[i]
+        c_i = ofb200.Context(local)
+        t_i = ofb200.StreamTracker(w, h, n_streams=n_i, ctx=c_i, **kw)
+        ha_i = torch.from_numpy(np.stack([pairs[j % distinct][0] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
+        hb_i = torch.from_numpy(np.stack([pairs[j % distinct][1] for j in range(bounds[i], bounds[i + 1])])).pin_memory()
+        dimu_i = torch.from_numpy(imu[bounds[i]:bounds[i + 1]].view(np.uint8).reshape(-1).copy()).cuda()
+        dres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        hres_i = torch.zeros(n_i * ofb200._lib.TRACK_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        subs.append((c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i))
+    torch.cuda.synchronize()
 
-        def estep(k):
-            for c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i in subs:
-                ofb200._lib.check(c_i.lib.ofb_tracker_step(t_i.h, P(hb_i if k & 1 else ha_i), w, w * h, P(dimu_i), None, P(dres_i),
-                                                           None, None, None, None))
-                ofb200._lib.check(c_i.lib.ofb_memcpy_async(c_i.h, P(hres_i), P(dres_i), hres_i.numel()))
-            for sub in subs:
-                sub[0].sync()
-        for k in range(2 * max(args.warmup, 1)):
-            estep(k)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for k in range(2 * args.steps):
-            estep(k)
-        torch.cuda.synchronize()
-        ems = (time.perf_counter() - t0) * 1e3
-        if dist is not None:
-            t = torch.tensor([ems], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ems = float(t.item())
-        eres = np.concatenate([sub[6].numpy().view(ofb200._lib.TRACK_RESULT_DTYPE) for sub in subs])
+    def estep(k):
+        for c_i, t_i, ha_i, hb_i, dimu_i, dres_i, hres_i in subs:
+            ofb200._lib.check(c_i.lib.ofb_tracker_step(t_i.h, P(hb_i if k & 1 else ha_i), w, w * h, P(dimu_i), None, P(dres_i),
+                                                       None, None, None, None))
+            ofb200._lib.check(c_i.lib.ofb_memcpy_async(c_i.h, P(hres_i), P(dres_i), hres_i.numel()))
         for sub in subs:
-            sub[1].close()
-        lifecycle["e2e"] = {"value": 256 * 2 * args.steps / (ems * 1e-3), "unit": "pairs/s", "ms_per_step": ems / (2 * args.steps),
-                            "h2d_bytes_per_step": B * w * h, "d2h_bytes_per_step": B * ofb200._lib.TRACK_RESULT_DTYPE.itemsize,
-                            "sub_fleets": NSUB, "check": {"min_tracked": int(eres["n_tracked"].min()), "solved": int((eres["flags"] & 1).sum())}}
-        line = {"metric": "fleet 1280x720 frame-pairs/s (256 streams)", "lifecycle": lifecycle, "value": 256 * args.steps / (ms * 1e-3), "unit": "pairs/s",
-                "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "config": {"workload": "C5: 256 streams x 1280x720, 500 features, maxLevel 3, stream-sharded", "streams_per_gpu": B},
-                "check": {"min_tracked": int(res["n_tracked"].min())}}
-    if rank == 0:
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+            sub[0].sync()
+    for k in range(2 * max(args.warmup, 1)):
+        estep(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(2 * args.steps):
+        estep(k)
+    torch.cuda.synchronize()
+    ems = maxr((time.perf_counter() - t0) * 1e3)
+    eres = np.concatenate([sub[6].numpy().view(ofb200._lib.TRACK_RESULT_DTYPE) for sub in subs])
+    for sub in subs:
+        sub[1].close(); sub[0].close()
+    lifecycle["e2e"] = {"value": FLEET * 2 * args.steps / (ems * 1e-3), "unit": "pairs/s", "ms_per_step": ems / (2 * args.steps),
+                        "h2d_bytes_per_step": FLEET * w * h, "d2h_bytes_per_step": FLEET * ofb200._lib.TRACK_RESULT_DTYPE.itemsize,
+                        "sub_fleets": NSUB, "check": {"min_tracked": int(eres["n_tracked"].min()), "solved": int((eres["flags"] & 1).sum())}}
+    out = {"metric": "fleet 1280x720 frame-pairs/s (%d streams, detect+track+solve per pair)" % FLEET,
+           "value": FLEET * args.steps / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "strong", "lifecycle": lifecycle,
+           "config": {"workload": "C5: %d streams x 1280x720, 500 features, maxLevel 3, stream-sharded over the ranks" % FLEET,
+                      "streams_per_gpu": B},
+           "check": {"min_tracked": int(res["n_tracked"].min())}}
+    return out, pairs
+
+
+def feature_tie_audit(ofb200, ctx, pairs, cfg):
+    """Parity spot check of what was timed: the detector's feature lists of the distinct frames against
+    cv2.goodFeaturesToTrack -- identical, or differing only by the documented float ties (tests/tie_rule.py)."""
+    try:
+        import cv2
+        from tie_rule import explain_by_ties
+    except Exception as e:
+        return {"unavailable": repr(e)[:100]}
+    frames = np.stack([p[0] for p in pairs]); nxt = np.stack([p[1] for p in pairs])
+    imu = imu_array(ofb200, pairs, len(pairs))
+    res, pp, pn, st = ofb200.frame_pairs(frames, nxt, imu, cfg, want_tracks=True, ctx=ctx)
+    out = {"frames": len(pairs), "identical": 0, "tie_groups": 0, "unexplained": 0}
+    for i, p in enumerate(pairs):
+        ref = cv2.goodFeaturesToTrack(p[0], cfg.max_corners, cfg.quality, cfg.min_distance, blockSize=cfg.block_size)
+        try:
+            g = explain_by_ties(pp[i, :int(res["n_features"][i])], ref, cv2.cornerMinEigenVal(p[0], cfg.block_size))
+            out["identical" if g == 0 else "tie_groups"] += 1 if g == 0 else g
+        except AssertionError:
+            out["unexplained"] += 1
+    return out
 
 
 def main():
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     args = parse()
+    if args.cpu_job:
+        return cpu_job_main(args)
     if args.impl == "reference":
         return reference_arm(args)
-    if args.workload != "c2":
-        return extra_workload(args)
     import torch
     import ofb200
     rank = int(os.environ.get("RANK", "0"))
@@ -470,8 +667,48 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    bind_near_gpu(local)
+    affinity = bind_near_gpu(local)              # BEFORE any pinned allocation: first touch decides the NUMA node
     ctx = ofb200.Context(local)
+    ncores = len(os.sched_getaffinity(0))
+
+    def finish(line, cpu_jobs):
+        """collectives are over: tear the group down, then rank 0 alone times the CPU baselines and prints the line"""
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank != 0:
+            return
+        for job in cpu_jobs:
+            log("cpu baseline: " + getattr(job, "__name__", "job"))
+            try:
+                job()
+            except Exception as e:       # cv2 missing on the box, fork refused, ...
+                line.setdefault("cpu_baseline_errors", []).append(repr(e)[:160])
+        print(json.dumps(line))
+
+    # ---- single-configuration runs (kept for quick looks; the default line holds all of them) ----
+    if args.workload in ("c1", "c4"):
+        out, pairs = leg_latency(args, ofb200, torch, ctx, args.workload, rank)
+        w, h, feat, ml = GEOM[args.workload]
+
+        def cpu():
+            if not args.no_cpu:
+                v, n, split = cpu_pair_path(lambda k: pairs[k % len(pairs)], feat, ml, 3.0, ncores)
+                out["cpu_baseline"] = {"value": 1e3 / v, "unit": "ms per pair", "cores": ncores, "kind": "port",
+                                       "sample": "%d pairs, cv2 4.13 gftt+pyrLK with %d threads; ms gftt/LK/solve = %s; %s" %
+                                                 (n, ncores, [round(x, 2) for x in split], SOLVE_NOTE)}
+        out["n_gpus"] = 1
+        return finish(out, [cpu])
+    if args.workload == "c5":
+        out, pairs = leg_fleet(args, ofb200, torch, dist, ctx, rank, world, local)
+        out["n_gpus"] = world
+
+        def cpu():
+            if not args.no_cpu:
+                out["cpu_baseline"] = cpu_job_subprocess("fleet")
+        return finish(out, [cpu])
+
+    # ---- config 2: the headline ----
     B = args.batch
     pairs = make_data(args.distinct, rank)
     mo0 = pairs[0][2]
@@ -524,6 +761,12 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    def maxr(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # the GPU idled (clocks down) while the synthetic frames were generated on the host: spin it up first,
     # then the W warm-up steps of the contract
     for _ in range(30):
@@ -541,10 +784,8 @@ def main():
     ms = ctx.timer_stop()
     launches = ctx.launch_count() - l0
     barrier()
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = maxr(ms)
+    log("c2 resident timed")
     value = world * B * args.steps / (ms * 1e-3)
     # correctness of what was timed: results must be plausible velocities (forward pairs have an exact truth)
     res = np.zeros(B, ofb200._lib.RESULT_DTYPE)
@@ -560,10 +801,7 @@ def main():
         step_independent()
     ms_ind = ctx.timer_stop()
     barrier()
-    if dist is not None:
-        t = torch.tensor([ms_ind], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_ind = float(t.item())
+    ms_ind = maxr(ms_ind)
     res_i = np.zeros(B, ofb200._lib.RESULT_DTYPE)
     ctx.memcpy(res_i, d_res, res_i.nbytes)
     verr_i = max(np.abs(res_i["v"][i] - pairs[i % len(pairs)][2]["v"]).max() for i in range(B))
@@ -596,10 +834,7 @@ def main():
         step_track()
     ms_trk = ctx.timer_stop()
     barrier()
-    if dist is not None:
-        t = torch.tensor([ms_trk], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_trk = float(t.item())
+    ms_trk = maxr(ms_trk)
     res_k = np.zeros(B, ofb200._lib.RESULT_DTYPE)
     ctx.memcpy(res_k, d_res, res_k.nbytes)
     track_solve = {"value": world * B * args.steps / (ms_trk * 1e-3), "unit": "pairs/s", "ms_per_step": ms_trk / args.steps,
@@ -630,10 +865,7 @@ def main():
         step_lifecycle()
     ms_life = ctx.timer_stop()
     barrier()
-    if dist is not None:
-        t = torch.tensor([ms_life], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_life = float(t.item())
+    ms_life = maxr(ms_life)
     res_l = np.zeros(B + 1, ofb200._lib.TRACK_RESULT_DTYPE)
     ctx.memcpy(res_l, d_tres, res_l.nbytes)
     trk.close()
@@ -654,8 +886,9 @@ def main():
     stage_ms, calls = ctx.stage_times()
     ctx.set_profile(False)
     stage_ms = [s / max(calls, 1) for s in stage_ms]
+    skeys = ["pyramid", "eig_nms", "select", "lk", "solve"]
     names = ["pyramid(pyr_down_kernel x%d levels)" % MAX_LEVEL, "eig_march_kernel<false,7>", "select_kernel",
-             "lk_track_fast_kernel", "pair_solve_kernel"]
+             "lk_track_fast2_kernel", "pair_solve_kernel"]
     g = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(1, MAX_LEVEL + 1))
     nfeat = float(res["n_features"].mean())
     nlev = MAX_LEVEL + 1
@@ -665,17 +898,13 @@ def main():
            (21 * nfeat + nfeat * nlev * ((WIN[0] + 3) * (WIN[1] + 3) + (WIN[0] + 1) * (WIN[1] + 1))) * B,
            (17 * nfeat + 80) * B]
     dom = int(np.argmax(stage_ms))
-    # DRAM bytes per image of each stage's kernel(s) from the committed ncu --set full capture (profiles/)
-    traffic, issue_pct, winst = None, None, None
+    # DRAM bytes and warp instructions per image of each stage's kernel(s) from the committed ncu --set full capture
+    tj = {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = ["pyramid", "eig_nms", "select", "lk", "solve"][dom]
-        if tj.get(key) is not None:
-            traffic = float(tj[key]["dram_bytes_per_pair"]) * B
-            issue_pct = tj[key].get("issue_active_pct")
-            winst = tj[key].get("warp_inst_per_pair")
     except Exception:
         pass
+    traffic = float(tj[skeys[dom]]["dram_bytes_per_pair"]) * B if tj.get(skeys[dom]) else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -685,11 +914,10 @@ def main():
     ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                "stage_ms": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"], [round(s, 4) for s in stage_ms])),
-                "stage_gbs": dict(zip(["pyramid", "eig_nms", "select", "lk", "solve"],
-                                      [round(a / (s * 1e-3) / 1e9, 2) if s > 0 else None for a, s in zip(alg, stage_ms)])),
-                "issue_active_pct_ncu": issue_pct, "issue": None,
-                "note": "the two dominant kernels (lambda_min+NMS, LK) are warp-issue bound (ncu issue-active 77 % / 79 %), "
+                "stage_ms": dict(zip(skeys, [round(s, 4) for s in stage_ms])),
+                "stage_gbs": dict(zip(skeys, [round(a / (s * 1e-3) / 1e9, 2) if s > 0 else None for a, s in zip(alg, stage_ms)])),
+                "issue_active_pct_ncu": tj.get(skeys[dom], {}).get("issue_active_pct"), "issue": None,
+                "note": "the two dominant kernels (lambda_min+NMS, LK) are warp-issue bound (ncu issue-active 73 % / 80 %), "
                         "not HBM bound: their DRAM traffic is the image read once; see DESIGN.md section 6"}
 
     # end to end through the public API: pinned host frames in, host results out, every step
@@ -707,96 +935,113 @@ def main():
             dt = float(t_.item())
         return dt, r_
 
+    log("c2 stage profile done")
     e2e_s, r = e2e_run(lambda: ofb200.frame_sequence(h_seq, imu_seq, cfg, ctx=ctx))
+    log("c2 e2e sequence done")
     e2e_i, _ = e2e_run(lambda: ofb200.frame_pairs(h_prev, h_next, imu, cfg, ctx=ctx))
+    # copy-only ceiling measured the same way, all ranks copying at the same time: the same pinned buffer through one
+    # cudaMemcpyAsync per step and nothing else. e2e / this = how close the pipeline is to the host's H2D limit.
+    d_stage = torch.empty((B + 1) * P, dtype=torch.uint8, device="cuda")
+
+    def copy_only():
+        ctx.lib.ofb_memcpy_async(ctx.h, ofb200._lib.ptr(d_stage), ofb200._lib.ptr(h_seq), (B + 1) * P)
+        ctx.sync()
+        return None
+    log("c2 e2e independent done")
+    cpy_s, _ = e2e_run(copy_only)
+    del d_stage
     clk.__exit__()
+    h2d_gbs = (B + 1) * P * args.steps / e2e_s / 1e9
+    ceil_gbs = (B + 1) * P * args.steps / cpy_s / 1e9
     e2e = {"value": world * B * args.steps / e2e_s, "unit": "pairs/s",
            "h2d_bytes_per_step": int(world * ((B + 1) * P + imu_seq.nbytes)), "d2h_bytes_per_step": int(world * r.nbytes),
-           "h2d_gbs_per_gpu": round((B + 1) * P * args.steps / e2e_s / 1e9, 1)}
+           "h2d_gbs_per_gpu": round(h2d_gbs, 1), "h2d_ceiling_gbs_concurrent": round(ceil_gbs, 1),
+           "frac_of_copy_ceiling": round(h2d_gbs / ceil_gbs, 3),
+           "host": {"cpu_affinity": affinity, "pinned_numa_node": numa_node_of(h_seq), "ranks_copying_concurrently": world,
+                    "note": "h2d_ceiling = the same pinned frames through one plain cudaMemcpyAsync per step on every rank at "
+                            "once (slowest rank): what this host delivers to %d GPU(s) in parallel" % world}}
     independent = {"value": world * B * args.steps / (ms_ind * 1e-3), "ms_per_step": ms_ind / args.steps,
                    "e2e": world * B * args.steps / e2e_i, "h2d_bytes_per_step": int(world * (2 * B * P + imu.nbytes)),
                    "max_abs_v_error_vs_truth": float(verr_i),
                    "note": "same pairs as separate prev/next buffers (no frame shared between pairs)"}
-
-    # Monte-Carlo sweep, trial ranges sharded over the ranks, sums merged with one all-reduce
-    mc = None
-    if not args.no_mc:
-        sim = ofb200.simulation
-        steps, pos, flow, per_step = mc_workload(ofb200, args.mc_trials)
-        begin, count = sim.shard_range(per_step, rank, world)
-        # warm-up at full size (the GPU idles while the 800 step descriptors are built on the host and its
-        # clocks drop), then three timed repetitions of the whole 1e8-trial job; the median is reported
-        for _ in range(2):
-            sim.run_steps(steps, pos, flow, count, seed=1, trial_begin=begin, ctx=ctx)
-        barrier()
-        reps = []
-        t0 = time.perf_counter()
-        for _ in range(3):
-            ctx.timer_start()
-            sums = sim.run_steps(steps, pos, flow, count, seed=1, trial_begin=begin, ctx=ctx)
-            reps.append(ctx.timer_stop())
-        mc_wall = (time.perf_counter() - t0) / 3
-        mc_ms = float(np.median(reps))
-        if dist is not None:
-            sums = sim.merge_sums(sums, None, torch.device("cuda", local))
-            t = torch.tensor([mc_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            mc_ms = float(t.item())
-        # the same job without the analytic bound R (callers that only consume v_obs: every saved sweep but one)
-        reps_nr = []
-        for _ in range(3):
-            ctx.timer_start()
-            sim.run_steps(steps, pos, flow, count, seed=1, trial_begin=begin, ctx=ctx, want_R=False)
-            reps_nr.append(ctx.timer_stop())
-        nr_ms = float(np.median(reps_nr))
-        if dist is not None:
-            t = torch.tensor([nr_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            nr_ms = float(t.item())
-        mean, std, mR, n = sim.stats_from_sums(sums, steps)
-        total = float(n.sum())
-        flop = 140 * MC_POINTS + 300
-        mc = {"metric": "MC trials/s", "value": total / (mc_ms * 1e-3), "unit": "trials/s", "trials": total,
-              "points": MC_POINTS, "steps": len(steps), "axes": list(MC_AXES), "ms": mc_ms, "ms_reps": [round(r, 3) for r in reps], "wall_ms": mc_wall * 1e3,
-              "value_without_R": total / (nr_ms * 1e-3),
-              "scaling": "strong", "precision": "fp32 per-point, fp64 solve/statistics",
-              "fp32_tflops_alg": total * flop / (mc_ms * 1e-3) / 1e12, "fp32_peak_tflops": 74.4,
-              "check_mean_v_step0": [round(float(x), 4) for x in mean[0]]}
-
-    cpu = None
-    if rank == 0 and not args.no_cpu:
-        ncores = len(os.sched_getaffinity(0))
-        try:
-            v, n, split = cpu_pair_path(pairs, 12.0, ncores)
-            cpu = {"value": v, "unit": "pairs/s", "cores": ncores, "kind": "port",
-                   "sample": "%d pairs of the same workload: cv2 4.13 gftt+pyrLK + oracle port of the reference's Python "
-                             "solve_lgs, %d threads; ms gftt/LK/solve = %s" % (n, ncores, [round(s, 1) for s in split])}
-        except Exception as e:   # cv2 missing on the box
-            cpu = {"value": None, "unit": "pairs/s", "cores": ncores, "kind": "port", "sample": "unavailable: %r" % (e,)}
-
-    # the dominant kernel against the bound that actually limits it: warp-instruction issue (instruction count per
-    # pair from the committed ncu capture, live stage time, live SM clock, 4 schedulers per SM)
     clocks = clk.summary()
-    if winst and clocks.get("sm_mhz"):
+    # the two dominant kernels against the bound that actually limits them: warp-instruction issue (instruction count per
+    # pair from the committed ncu capture, live stage time, live SM clock, 4 schedulers per SM)
+    if clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         peak_i = sms * 4 * float(clocks["sm_mhz"]) * 1e6
-        ach_i = float(winst) * B / (stage_ms[dom] * 1e-3)
-        roofline["issue"] = {"achieved": ach_i, "peak": peak_i, "unit": "warp-instructions/s", "frac": ach_i / peak_i,
-                             "warp_inst_per_pair": winst}
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD,
-                           "pairs_per_step_per_gpu": B, "frames_per_step_per_gpu": B + 1, "distinct_motions": len(pairs),
-                           "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
-                           "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "independent_pairs": independent, "track_solve": track_solve, "lifecycle": lifecycle, "mc": mc,
-                "check": {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+        iss = {}
+        for key in ("eig_nms", "lk"):
+            wi = tj.get(key, {}).get("warp_inst_per_pair")
+            if wi:
+                ach_i = float(wi) * B / (stage_ms[skeys.index(key)] * 1e-3)
+                iss[key] = {"achieved": ach_i, "peak": peak_i, "unit": "warp-instructions/s", "frac": ach_i / peak_i,
+                            "warp_inst_per_pair": wi}
+        if iss:
+            roofline["issue"] = dict(iss.get(skeys[dom], {}), per_kernel=iss)
+
+    check = {"max_abs_v_error_vs_truth": float(verr), "min_tracked": tracked}
+
+    # ---- the other BASELINE configurations, same process, same box ----
+    c1 = c4 = c5 = mc = None
+    c1_pairs = c4_pairs = c5_pairs = None
+    log("c2 legs done")
+    if args.workload == "all" and not args.no_extra:
+        # free the C2 buffers first (the 4K / fleet legs allocate their own)
+        del d_prev, d_next, d_seq, d_pts
+        torch.cuda.empty_cache()
+        c1, c1_pairs = leg_latency(args, ofb200, torch, ctx, "c1", rank)
+        log("c1 done")
+        c4, c4_pairs = leg_latency(args, ofb200, torch, ctx, "c4", rank)
+        log("c4 done")
+        c5, c5_pairs = leg_fleet(args, ofb200, torch, dist, ctx, rank, world, local)
+        log("c5 done")
+    if not args.no_mc:
+        mc = leg_mc(args, ofb200, torch, dist, rank, world, local)
+        log("mc done")
+
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
+                       "pairs_per_step_per_gpu": B, "frames_per_step_per_gpu": B + 1, "distinct_motions": len(pairs),
+                       "l2": "inputs larger than L2 (%d MB of frames per step)" % ((B + 1) * P // 2 ** 20),
+                       "parallelism": "streams sharded, one batch per GPU, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "independent_pairs": independent, "track_solve": track_solve, "lifecycle": lifecycle, "mc": mc,
+            "c1": c1, "c4": c4, "c5": c5, "check": check}
+
+    # ---- CPU baselines: rank 0, after the last collective ----
+    def cpu_c2():
+        v, n, split = cpu_pair_path(lambda k: stream_pair(pairs, k), K_FEAT, MAX_LEVEL, 10.0, ncores)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": ncores, "kind": "port",
+                                "sample": "%d pairs of the same workload: cv2 4.13 gftt+pyrLK, %d threads; ms gftt/LK/solve = %s; %s" %
+                                          (n, ncores, [round(s, 1) for s in split], SOLVE_NOTE)}
+        check["feature_lists_vs_cv2"] = feature_tie_audit(ofb200, ctx, pairs, cfg)
+
+    def cpu_lat(out, prs, name):
+        def run():
+            w, h, feat, ml = GEOM[name]
+            v, n, split = cpu_pair_path(lambda k: prs[k % len(prs)], feat, ml, 3.0, ncores)
+            out["cpu_baseline"] = {"value": 1e3 / v, "unit": "ms per pair", "cores": ncores, "kind": "port",
+                                   "sample": "%d pairs, cv2 4.13 gftt+pyrLK with %d threads; ms gftt/LK/solve = %s; %s" %
+                                             (n, ncores, [round(x, 2) for x in split], SOLVE_NOTE)}
+        return run
+
+    def cpu_c5():
+        c5["cpu_baseline"] = cpu_job_subprocess("fleet")
+
+    def cpu_mc_job():
+        mc["cpu_baseline"] = cpu_job_subprocess("mc", int(mc["trials"]))
+
+    jobs = []
+    if not args.no_cpu:
+        jobs.append(cpu_c2)
+        if c1 is not None:
+            jobs += [cpu_lat(c1, c1_pairs, "c1"), cpu_lat(c4, c4_pairs, "c4"), cpu_c5]
+        if mc is not None:
+            jobs.append(cpu_mc_job)
+    finish(line, jobs)
 
 
 if __name__ == "__main__":

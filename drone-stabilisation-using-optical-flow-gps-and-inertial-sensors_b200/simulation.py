@@ -76,18 +76,31 @@ def _steps_array(steps):
 
 
 def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, precision="fp32", dump=False, ctx=None,
-              want_R=True):
+              want_R=True, sums_out=None):
     """Run `trials` trials of every step on this GPU. Returns the per-step sums (structured array
-    _lib.MCSUMS_DTYPE) and, when dump, v_obs (S,trials,3) and R (S,trials)."""
+    _lib.MCSUMS_DTYPE) and, when dump, v_obs (S,trials,3) and R (S,trials).
+    sums_out: a DEVICE buffer (CUDA tensor of len(steps) x 8 float64, or an address) that receives the sums instead; the
+    call then only enqueues (no host synchronisation), so a collective on the same stream can follow it directly."""
     ctx = ctx or _lib.default_context()
     trials = int(trials)
     if trials <= 0:
         raise ValueError(' iterations must be a positive number')
-    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
-    flow = np.ascontiguousarray(flow, dtype=np.float64).reshape(-1, 2)
-    if pos.shape != flow.shape:
-        raise ValueError("pos and true_flow must have the same shape")
-    arr = _steps_array(steps)
+    if hasattr(pos, "data_ptr"):              # device-resident point arrays (CUDA tensors, (N,2) float64): used in place
+        if tuple(pos.shape) != tuple(flow.shape) or len(pos.shape) != 2 or pos.shape[1] != 2:
+            raise ValueError("pos and true_flow must both be (N,2)")
+    else:
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        flow = np.ascontiguousarray(flow, dtype=np.float64).reshape(-1, 2)
+        if pos.shape != flow.shape:
+            raise ValueError("pos and true_flow must have the same shape")
+    arr = steps if isinstance(steps, C.Array) else _steps_array(steps)
+    if sums_out is not None:
+        if dump:
+            raise ValueError("sums_out (device-resident sums) and dump are exclusive")
+        _lib.check(ctx.lib.ofb_mc_sweep(ctx.h, C.cast(arr, C.c_void_p), len(steps), int(step_id_base), _lib.ptr(pos),
+                                        _lib.ptr(flow), len(pos), int(trial_begin), trials, int(seed) & (2 ** 64 - 1),
+                                        PRECISIONS[precision] + (0 if want_R else 2), _lib.ptr(sums_out), None, None))
+        return sums_out
     sums = np.zeros(len(steps), _lib.MCSUMS_DTYPE)
     vd = Rd = None
     if dump:
