@@ -578,6 +578,34 @@ def leg_fleet(args, ofb200, torch, dist, ctx, rank, world, local):
                          "(masked top-up when <= %d points survive); resident frames used in place (borrow_frames)" % (feat // 2),
                  "check": {"min_tracked": int(tres["n_tracked"].min()), "min_points": int(tres["n_points"].min()),
                            "solved": int((tres["flags"] & 1).sum()), "topups_last_step": int((tres["n_added"] > 0).sum())}}
+    # BGR fleets (velocity_measurment_node:113 converts every frame): the conversion is fused into the first pyramid step
+    # (grey level 0 written once, level 1 from the same read); OFB_BGR_FUSED=0 = the separate conversion kernel of round 1
+    bgr_a = torch.stack([a, a, a], dim=-1).contiguous(); bgr_b = torch.stack([b, b, b], dim=-1).contiguous()
+    trk = ofb200.StreamTracker(w, h, n_streams=B, bgr=True, ctx=ctx, **kw)
+
+    def bstep(k):
+        ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(bgr_b if k & 1 else bgr_a), 3 * w, 3 * w * h, P(d_imu), None, P(d_tres),
+                                                   None, None, None, None))
+    bms = {}
+    for mode in ("1", "0"):
+        os.environ["OFB_BGR_FUSED"] = mode
+        for k in range(2 * max(args.warmup, 1)):
+            bstep(k)
+        barrier()
+        ctx.timer_start()
+        for k in range(2 * args.steps):
+            bstep(k)
+        bms[mode] = maxr(ctx.timer_stop()) / (2 * args.steps)
+    os.environ.pop("OFB_BGR_FUSED", None)
+    tres_b = np.zeros(B, ofb200._lib.TRACK_RESULT_DTYPE); ctx.memcpy(tres_b, d_tres, tres_b.nbytes)
+    trk.close()
+    del bgr_a, bgr_b
+    lifecycle["bgr_frames"] = {"value": FLEET / (bms["1"] * 1e-3), "unit": "pairs/s", "ms_per_step": bms["1"],
+                               "ms_per_step_separate_conversion": bms["0"],
+                               "dram_bytes_not_moved_per_frame": w * h,
+                               "what": "the same lifecycle fed BGR8 frames: BGR->grey fused into the level-0 -> level-1 kernel (the grey "
+                                       "level 0 is written once and not read back for level 1)",
+                               "check": {"min_tracked": int(tres_b["n_tracked"].min()), "solved": int((tres_b["flags"] & 1).sum())}}
     # end to end: the fleet's frames arrive in (pinned) HOST memory every step. Four sub-fleets on four contexts (own
     # streams): the H2D copy of one sub-fleet overlaps the kernels of the others; every step's result records are read
     # back to the host. Bytes per step: B frames in, B result records out.

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "ofb_memcpy_async": (i32, [vp, vp, vp, sz]),
     "ofb_bgr2gray": (i32, [vp, vp, i32, i32, i32, vp, i32]),
     "ofb_pyramid": (i32, [vp, vp, i32, i32, i32, sz, i32, i32, C.POINTER(vp)]),
+    "ofb_pyramid_bgr": (i32, [vp, vp, i32, i32, i32, sz, i32, i32, C.POINTER(vp)]),
     "ofb_pyr_free": (i32, [vp, vp]),
     "ofb_pyr_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "ofb_pyr_download": (i32, [vp, vp, i32, i32, vp, i32]),
@@ -127,6 +128,7 @@ _SIGNATURES = {
     "ofb_tracker_graph_info": (i32, [vp, C.POINTER(u64), C.POINTER(i32)]),
     "ofb_tracker_render_mask": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "ofb_mc_sweep": (i32, [vp, vp, i32, i32, vp, vp, i32, u64, u64, u64, i32, vp, vp, vp]),
+    "ofb_mc_sweep_multi": (i32, [vp, i32, vp, i32, i32, vp, vp, i32, u64, u64, u64, i32, vp]),
     "ofb_mc_feas": (i32, [vp, vp, i32, vp, vp, u64, u64, u64, vp]),
     "ofb_minmax": (i32, [vp, vp, sz, C.POINTER(f64), C.POINTER(f64)]),
     "ofb_histogram": (i32, [vp, vp, sz, f64, f64, i32, vp]),

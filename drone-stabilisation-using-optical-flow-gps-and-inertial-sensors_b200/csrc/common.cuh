@@ -204,6 +204,8 @@ static inline int ofb_ensure_smem(ofb_ctx* ctx, int slot, F func, size_t smem)
 
 // stage entry points implemented in the per-stage translation units (device pointers only)
 int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* pyr);
+int ofb_pyr_build_from(ofb_ctx* ctx, ofb_pyr* pyr, int first_level);
+int ofb_pyr_ingest_bgr(ofb_ctx* ctx, ofb_pyr* pyr, const uint8_t* bgr, int bpitch, size_t bstride);
 int ofb_pyr_alloc(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_images,
                   int max_level, ofb_pyr** out);
 int ofb_pyr_prepare(ofb_ctx* ctx, ofb_pyr** slot, const uint8_t* img, int w, int h, int pitch, size_t image_stride,

@@ -430,6 +430,52 @@ extern "C" int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps,
     return ofb_finish_out(ctx, o, 3);
 }
 
+// Single-process multi-GPU sweep (SURVEY 8b proposed ofb_mc_sweep(ctx_list, n_ctx, ...)): the trial range is cut into
+// contiguous shards, one per context (any mix of devices), every shard is enqueued before the first one is waited for,
+// and the per-step sums are merged on the host in context order -- the counter RNG makes the union identical to a
+// one-context run up to fp64 summation order. A ctypes-only consumer gets all GPUs of a box without torch or NCCL;
+// multi-PROCESS runs (one rank per GPU) merge the same 8 doubles per step with one all-reduce instead (simulation.py).
+extern "C" int ofb_mc_sweep_multi(ofb_ctx** ctxs, int n_ctx, const ofb_mc_step* steps, int n_steps, int step_id_base,
+                                  const double* pos, const double* true_flow, int total_points,
+                                  uint64_t trial_begin, uint64_t trials, uint64_t seed, int precision,
+                                  ofb_mc_sums* sums_out)
+{
+    OFB_REQUIRE(ctxs && n_ctx >= 1 && n_ctx <= 64, "mc_sweep_multi: needs 1..64 contexts");
+    OFB_REQUIRE(steps && pos && true_flow && sums_out, "mc_sweep_multi: null argument");
+    OFB_REQUIRE(n_steps > 0 && n_steps <= 65535, "mc_sweep_multi: n_steps must be in 1..65535");
+    OFB_REQUIRE(trials > 0, "mc_sweep: iterations must be a positive number");
+    OFB_REQUIRE(!ofb_is_device_ptr(sums_out) && !ofb_is_device_ptr(pos) && !ofb_is_device_ptr(true_flow),
+                "mc_sweep_multi: pos, true_flow and sums_out must be host memory (they are read / merged for several devices)");
+    for (int c = 0; c < n_ctx; ++c) OFB_REQUIRE(ctxs[c], "mc_sweep_multi: null context %d", c);
+    const uint64_t base = trials / (uint64_t)n_ctx, rem = trials % (uint64_t)n_ctx;
+    std::vector<uint64_t> cnt(n_ctx);
+    uint64_t begin = trial_begin;
+    for (int c = 0; c < n_ctx; ++c) {                       // enqueue every shard (device-resident sums: no wait)
+        cnt[c] = base + ((uint64_t)c < rem ? 1 : 0);
+        if (cnt[c] == 0) continue;
+        ofb_ctx* ctx = ctxs[c];
+        OFB_CUDA(cudaSetDevice(ctx->device));
+        OFB_TRY(ctx->scratch[SC_MC2].reserve(sizeof(ofb_mc_sums) * n_steps));
+        OFB_TRY(ofb_mc_sweep(ctx, steps, n_steps, step_id_base, pos, true_flow, total_points, begin, cnt[c], seed, precision,
+                             ctx->scratch[SC_MC2].as<ofb_mc_sums>(), nullptr, nullptr));
+        begin += cnt[c];
+    }
+    std::vector<ofb_mc_sums> part((size_t)n_steps);
+    memset(sums_out, 0, sizeof(ofb_mc_sums) * n_steps);
+    for (int c = 0; c < n_ctx; ++c) {                       // merge in context order: a fixed summation order
+        if (cnt[c] == 0) continue;
+        ofb_ctx* ctx = ctxs[c];
+        OFB_CUDA(cudaSetDevice(ctx->device));
+        OFB_CUDA(cudaMemcpyAsync(part.data(), ctx->scratch[SC_MC2].p, sizeof(ofb_mc_sums) * n_steps, cudaMemcpyDeviceToHost, ctx->stream));
+        OFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n_steps; ++i) {
+            sums_out[i].n += part[i].n; sums_out[i].sum_R += part[i].sum_R;
+            for (int k = 0; k < 3; ++k) { sums_out[i].sum_dv[k] += part[i].sum_dv[k]; sums_out[i].sum_dv2[k] += part[i].sum_dv2[k]; }
+        }
+    }
+    return OFB_OK;
+}
+
 extern "C" int ofb_mc_feas(ofb_ctx* ctx, const ofb_mc_step* step, int step_id, const double* pos,
                            const double* true_flow, uint64_t trial_begin, uint64_t trials, uint64_t seed,
                            double* sums_out)

@@ -179,6 +179,99 @@ pyr_down_small_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitc
     pyr_filter_tile(tile, dst + (size_t)blockIdx.z * dstride, X0, Y0, dw, dh, dpitch);
 }
 
+// BGR frames (cv2.cvtColor(frame, COLOR_BGR2GRAY) at velocity_measurment_node:113 in front of the pyramid): one kernel
+// converts the source footprint of a level-1 tile to grey in shared memory, writes the tile's own 128x64 block of the
+// grey level 0 (LK tracks on it) and filters level 1 from shared memory -- the grey image is written once and never
+// read back for the first pyramid level (the separate ingest + pyr_down pair wrote P and re-read P bytes per frame).
+// A 16-pixel group is 48 BGR bytes = three 128-bit loads; a pixel's (B, G, R) is re-aligned to the low bytes of a word
+// with one funnel shift and weighted by two dp2a: (3735 B + 19235 G) + (9798 R) + 2^14 >> 15, cv2's fixed-point rule.
+__device__ __forceinline__ int dp2a_lo_u(unsigned int w16x2, unsigned int bytes, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_u(unsigned int w16x2, unsigned int bytes, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w16x2), "r"(bytes), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned int bgr_to_gray_word(unsigned int px)      // bytes 0..2 = B, G, R (byte 3 ignored)
+{
+    int v = dp2a_lo_u(3735u | (19235u << 16), px, 1 << 14);
+    v = dp2a_hi_u(9798u, px, v);                                               // 9798 R + 0 * byte 3
+    return (unsigned int)v >> 15;
+}
+
+__global__ void __launch_bounds__(256)
+ingest_bgr_pyr_kernel(const uint8_t* __restrict__ bgr, int w, int h, int bpitch, size_t bstride,
+                      uint8_t* __restrict__ gray, int gpitch, size_t gstride,
+                      uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride)
+{
+    __shared__ __align__(16) uint8_t tile[PS_H * PS_PITCH];
+    const uint8_t* __restrict__ src = bgr + (size_t)blockIdx.z * bstride;
+    uint8_t* __restrict__ g0 = gray + (size_t)blockIdx.z * gstride;
+    const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
+    const int sx0 = 2 * X0 - 16, sy0 = 2 * Y0 - 2;                 // source pixel of tile[0][0]
+    const bool aligned = ((bpitch & 15) == 0) && ((((size_t)src) & 15) == 0) && ((gpitch & 15) == 0) && ((((size_t)g0) & 15) == 0);
+    constexpr int GPR = PS_W / 16;                                 // 16-pixel groups per tile row
+    // groups 1 .. GPR-2 = the tile's own 128 columns; of the two outer groups the filter reads only the last two /
+    // the first pixel (see pyr_stage_tile), handled below
+    for (int i = threadIdx.x; i < PS_H * (GPR - 2); i += 256) {
+        const int r = i / (GPR - 2), c = 1 + i - r * (GPR - 2);
+        const int y = sy0 + r, gx0 = sx0 + 16 * c;
+        const int yy = refl101_bf(y, h);
+        const uint8_t* __restrict__ row = src + (size_t)yy * bpitch;
+        unsigned int out[4];
+        if (aligned && gx0 + 16 <= w) {                            // (gx0 >= 0 for these groups)
+            const uint4* __restrict__ q = (const uint4*)(row + 3 * gx0);
+            const uint4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
+            const unsigned int wd[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w, 0u};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned int packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int p = 4 * j + k, byte = 3 * p;          // pixel p starts at byte 3p of the 48-byte group
+                    const unsigned int px = __funnelshift_r(wd[byte >> 2], wd[(byte >> 2) + 1], 8 * (byte & 3));
+                    packed |= bgr_to_gray_word(px) << (8 * k);
+                }
+                out[j] = packed;
+            }
+        } else {                                                   // right image edge: per pixel, reflect-101 columns
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned int packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint8_t* __restrict__ p = row + 3 * refl101_bf(gx0 + 4 * j + k, w);
+                    const unsigned int px = (unsigned int)__ldg(p) | ((unsigned int)__ldg(p + 1) << 8) | ((unsigned int)__ldg(p + 2) << 16);
+                    packed |= bgr_to_gray_word(px) << (8 * k);
+                }
+                out[j] = packed;
+            }
+        }
+        *(uint4*)(tile + r * PS_PITCH + 16 * c) = make_uint4(out[0], out[1], out[2], out[3]);
+        // this tile's own block of the grey level 0: source rows 2Y0 .. 2Y0+63 of these columns
+        if (r >= 2 && r < PS_H - 1 && y < h && gx0 < w) {
+            uint8_t* __restrict__ o = g0 + (size_t)y * gpitch + gx0;
+            if (aligned && gx0 + 16 <= w) *(uint4*)o = make_uint4(out[0], out[1], out[2], out[3]);
+            else
+                for (int k = 0; k < 16 && gx0 + k < w; ++k) o[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+    for (int i = threadIdx.x; i < PS_H * 3; i += 256) {            // halo columns: tile bytes 14, 15 and 144
+        const int r = i / 3, e = i - r * 3;
+        const int j = e < 2 ? 14 + e : 16 * (GPR - 1);
+        const uint8_t* __restrict__ p = src + (size_t)refl101_bf(sy0 + r, h) * bpitch + 3 * refl101_bf(sx0 + j, w);
+        const unsigned int px = (unsigned int)__ldg(p) | ((unsigned int)__ldg(p + 1) << 8) | ((unsigned int)__ldg(p + 2) << 16);
+        tile[r * PS_PITCH + j] = (uint8_t)bgr_to_gray_word(px);
+    }
+    __syncthreads();
+    pyr_filter_tile(tile, dst + (size_t)blockIdx.z * dstride, X0, Y0, dw, dh, dpitch);
+}
+
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with two shared-
 // memory stages: the TMA copy of tile i+1 is in flight while tile i is filtered.
 __global__ void __launch_bounds__(256)
@@ -262,9 +355,26 @@ static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
     return fn;
 }
 
-int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p)
+int ofb_pyr_build_device(ofb_ctx* ctx, ofb_pyr* p) { return ofb_pyr_build_from(ctx, p, 1); }
+
+// Fused first step for BGR frames: grey level 0 (into `gray`, which must be the pyramid's level 0) and level 1 from one
+// read of the BGR frames, then the remaining levels as usual. Images too small for the fused tile kernel's single
+// reflection (or pyramids without a level 1) are converted by the caller and built with ofb_pyr_build_device.
+int ofb_pyr_ingest_bgr(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* bgr, int bpitch, size_t bstride)
 {
-    for (int l = 1; l < p->n_levels; ++l) {
+    OFB_REQUIRE(p->n_levels >= 2 && p->w[0] >= 4 && p->h[0] >= 4, "pyr_ingest_bgr: needs a level 1 and an image of at least 4x4");
+    const int tiles_x = ofb_div_up(p->w[1], PT_W), tiles_y = ofb_div_up(p->h[1], PT_H);
+    dim3 g3(tiles_x, tiles_y, p->n_active);
+    ingest_bgr_pyr_kernel<<<g3, 256, 0, ctx->stream>>>(bgr, p->w[0], p->h[0], bpitch, bstride, (uint8_t*)p->level0, p->level0_pitch,
+                                                      p->level0_stride, p->base + p->level_off[1], p->w[1], p->h[1], p->pitch[1],
+                                                      p->image_stride[1]);
+    OFB_LAUNCH_CHECK(ctx);
+    return ofb_pyr_build_from(ctx, p, 2);
+}
+
+int ofb_pyr_build_from(ofb_ctx* ctx, ofb_pyr* p, int first_level)
+{
+    for (int l = first_level; l < p->n_levels; ++l) {
         const uint8_t* s; int sp; size_t ss;
         if (l == 1) { s = p->level0; sp = p->level0_pitch; ss = p->level0_stride; }
         else { s = p->base + p->level_off[l - 1]; sp = p->pitch[l - 1]; ss = p->image_stride[l - 1]; }
@@ -326,12 +436,12 @@ static int pyr_upload_level0(ofb_ctx* ctx, ofb_pyr* p, const uint8_t* img, int p
 // Allocates the pyramid object and its level storage. When `img` is device memory level 0 aliases
 // it (the caller keeps it alive while the pyramid is in use); host images are copied in.
 static int ofb_pyr_alloc_cap(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride, int n_active,
-                             int n_images, int max_level, ofb_pyr** out)
+                             int n_images, int max_level, ofb_pyr** out, bool upload = true)
 {
     ofb_pyr* p = new ofb_pyr();
     p->n_images = n_images;
     p->n_active = n_active;
-    bool dev = ofb_is_device_ptr(img);
+    bool dev = upload && ofb_is_device_ptr(img);         // (!upload: level 0 is owned and filled by a kernel)
     int lw = w, lh = h, nl = 1;
     p->w[0] = w; p->h[0] = h;
     for (int l = 1; l <= max_level && l < OFB_MAX_LEVELS; ++l) {
@@ -362,7 +472,7 @@ static int ofb_pyr_alloc_cap(ofb_ctx* ctx, const uint8_t* img, int w, int h, int
     } else {
         p->level0 = p->base + p->level_off[0]; p->level0_pitch = p->pitch[0]; p->level0_stride = p->image_stride[0];
         p->level0_owned = true;
-        int r = pyr_upload_level0(ctx, p, img, pitch, image_stride);
+        int r = upload ? pyr_upload_level0(ctx, p, img, pitch, image_stride) : OFB_OK;
         if (r != OFB_OK) { cudaFree(p->base); delete p; return r; }
     }
     *out = p;
@@ -411,6 +521,40 @@ extern "C" int ofb_pyramid(ofb_ctx* ctx, const uint8_t* img, int w, int h, int p
     ofb_pyr* p = nullptr;
     OFB_TRY(ofb_pyr_alloc(ctx, img, w, h, pitch, image_stride, n_images, max_level, &p));
     int r = ofb_pyr_build_device(ctx, p);
+    if (r != OFB_OK) { cudaFree(p->base); delete p; return r; }
+    ctx->pyramids.push_back(p);
+    *out = p;
+    return OFB_OK;
+}
+
+extern "C" int ofb_pyramid_bgr(ofb_ctx* ctx, const uint8_t* bgr, int w, int h, int pitch, size_t image_stride,
+                               int n_images, int max_level, ofb_pyr** out)
+{
+    OFB_REQUIRE(ctx && bgr && out, "pyramid_bgr: null argument");
+    OFB_REQUIRE(w > 0 && h > 0 && pitch >= 3 * w, "pyramid_bgr: bad image geometry %dx%d pitch %d", w, h, pitch);
+    OFB_REQUIRE(n_images > 0 && n_images <= 65535, "pyramid_bgr: n_images must be in 1..65535");
+    OFB_REQUIRE(max_level >= 0, "pyramid_bgr: max_level must be >= 0");
+    OFB_REQUIRE(n_images == 1 || image_stride >= (size_t)pitch * (h - 1) + 3 * (size_t)w, "pyramid_bgr: image_stride too small");
+    OFB_CUDA(cudaSetDevice(ctx->device));
+    const void* dsrc;
+    const size_t bytes = image_stride * (size_t)(n_images - 1) + (size_t)pitch * (h - 1) + 3 * (size_t)w;
+    OFB_TRY(ofb_stage_in(ctx, SC_FRAMES, bgr, bytes, &dsrc));
+    ofb_pyr* p = nullptr;
+    OFB_TRY(ofb_pyr_alloc_cap(ctx, nullptr, w, h, 0, 0, n_images, n_images, max_level, &p, false));
+    int r;
+    if (p->n_levels >= 2 && w >= 4 && h >= 4) r = ofb_pyr_ingest_bgr(ctx, p, (const uint8_t*)dsrc, pitch, image_stride);
+    else {
+        // no level 1 (or a tiny image): plain conversion, then the generic level kernels
+        r = OFB_OK;
+        for (int i = 0; i < n_images && r == OFB_OK; ++i) {
+            dim3 grid(ofb_div_up(w, 256), h);
+            bgr2gray_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)dsrc + (size_t)i * image_stride, w, h, pitch,
+                                                          (uint8_t*)p->level0 + (size_t)i * p->level0_stride, p->level0_pitch);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) { ofb_set_error("pyramid_bgr: conversion launch failed"); r = OFB_E_CUDA; }
+        }
+        if (r == OFB_OK) r = ofb_pyr_build_device(ctx, p);
+    }
     if (r != OFB_OK) { cudaFree(p->base); delete p; return r; }
     ctx->pyramids.push_back(p);
     *out = p;

@@ -445,6 +445,7 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     const uint8_t* f = t->frames[t->cur].as<uint8_t>();
     uint8_t* fown = t->frames[t->cur].as<uint8_t>();
     int fpitch = t->pitch_d; size_t fstride = t->stride_d;
+    bool fused_bgr = false; const uint8_t* bgr_src = nullptr; int bgr_pitch = 0; size_t bgr_stride = 0;
     if (cfg.bgr_input) {
         const uint8_t* src = frames; int spitch = pitch; size_t sstride = image_stride;
         if (!ofb_is_device_ptr(frames)) {
@@ -455,10 +456,17 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
                                            pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
             src = t->bgr.as<uint8_t>();
         }
-        const int vec = ((uintptr_t)src % 4 == 0 && spitch % 4 == 0 && sstride % 4 == 0) ? 1 : 0;
-        dim3 grid(ofb_div_up(ofb_div_up(w, 4), 128), h, S);
-        ingest_bgr_kernel<<<grid, 128, 0, ctx->stream>>>(src, w, h, spitch, sstride, fown, t->pitch_d, t->stride_d, vec);
-        OFB_LAUNCH_CHECK(ctx);
+        // the conversion is fused into the first pyramid step (grey level 0 and level 1 from one read of the BGR frame)
+        // whenever there is a level 1; OFB_BGR_FUSED=0 keeps the separate conversion kernel (cross-check)
+        const char* fe = getenv("OFB_BGR_FUSED");
+        fused_bgr = pc.max_level >= 1 && w >= 4 && h >= 4 && !(fe && fe[0] == '0');
+        if (fused_bgr) { bgr_src = src; bgr_pitch = spitch; bgr_stride = sstride; }
+        else {
+            const int vec = ((uintptr_t)src % 4 == 0 && spitch % 4 == 0 && sstride % 4 == 0) ? 1 : 0;
+            dim3 grid(ofb_div_up(ofb_div_up(w, 4), 128), h, S);
+            ingest_bgr_kernel<<<grid, 128, 0, ctx->stream>>>(src, w, h, spitch, sstride, fown, t->pitch_d, t->stride_d, vec);
+            OFB_LAUNCH_CHECK(ctx);
+        }
     } else if (cfg.borrow_frames && ofb_is_device_ptr(frames)) {
         f = frames; fpitch = pitch; fstride = image_stride;
     } else if (pitch == t->pitch_d && (S == 1 || image_stride == t->stride_d)) {
@@ -468,7 +476,8 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
             OFB_CUDA(cudaMemcpy2DAsync(fown + (size_t)s * t->stride_d, t->pitch_d, frames + (size_t)s * image_stride, pitch, w, h,
                                        cudaMemcpyDefault, ctx->stream));
     }
-    OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, fpitch, fstride, S, S, pc.max_level, true));
+    OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, fpitch, fstride, S, S, pc.max_level, !fused_bgr));
+    if (fused_bgr) OFB_TRY(ofb_pyr_ingest_bgr(ctx, t->pyr[t->cur], bgr_src, bgr_pitch, bgr_stride));
     int* count = t->counts.as<int>();
     int* need = count + S;
     int* keptn = count + 2 * S;

@@ -114,6 +114,28 @@ def run_steps(steps, pos, flow, trials, seed=0, step_id_base=0, trial_begin=0, p
     return sums
 
 
+def run_steps_multi(steps, pos, flow, trials, ctxs, seed=0, step_id_base=0, trial_begin=0, precision="fp32", want_R=True):
+    """One process, several GPUs: `ctxs` is a list of Contexts (one per device, or several per device); the trial range is
+    sharded over them inside the library (ofb_mc_sweep_multi) and the sums come back merged. No torch.distributed."""
+    trials = int(trials)
+    if trials <= 0:
+        raise ValueError(' iterations must be a positive number')
+    if not ctxs:
+        raise ValueError("at least one context is required")
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    flow = np.ascontiguousarray(flow, dtype=np.float64).reshape(-1, 2)
+    if pos.shape != flow.shape:
+        raise ValueError("pos and true_flow must have the same shape")
+    arr = steps if isinstance(steps, C.Array) else _steps_array(steps)
+    handles = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    sums = np.zeros(len(steps), _lib.MCSUMS_DTYPE)
+    _lib.check(ctxs[0].lib.ofb_mc_sweep_multi(handles, len(ctxs), C.cast(arr, C.c_void_p), len(steps), int(step_id_base),
+                                              _lib.ptr(pos), _lib.ptr(flow), len(pos), int(trial_begin), trials,
+                                              int(seed) & (2 ** 64 - 1), PRECISIONS[precision] + (0 if want_R else 2),
+                                              _lib.ptr(sums)))
+    return sums
+
+
 def shard_range(total, rank, world):
     """Contiguous trial range of `rank`: [begin, begin+count)."""
     base, rem = divmod(int(total), int(world))

@@ -42,18 +42,24 @@ def cvtColor(src, code=COLOR_BGR2GRAY, ctx=None):
 class Pyramid:
     """Device-resident Gaussian pyramid(s) of n_images same-sized frames (ofb_pyr)."""
 
-    def __init__(self, images, max_level, ctx=None):
+    def __init__(self, images, max_level, ctx=None, bgr=False):
+        """bgr=True: images are BGR8 frames (H,W,3) / (N,H,W,3); the grey conversion (cv2.cvtColor at
+        velocity_measurment_node:113) is fused into the first pyramid step (ofb_pyramid_bgr)."""
         self.ctx = ctx or _lib.default_context()
         a = np.asarray(images)
-        if a.dtype != np.uint8 or a.ndim not in (2, 3):
-            raise ValueError("images must be uint8 (H,W) or (N,H,W)")
+        nd = (3, 4) if bgr else (2, 3)
+        if a.dtype != np.uint8 or a.ndim not in nd or (bgr and a.shape[-1] != 3):
+            raise ValueError("images must be uint8 (H,W) or (N,H,W)" + (" with 3 channels last" if bgr else ""))
         a = np.ascontiguousarray(a)
-        if a.ndim == 2:
+        if a.ndim == nd[0]:
             a = a[None]
-        n, h, w = a.shape
+        n, h, w = a.shape[:3]
         self._keep = a
         hdl = C.c_void_p()
-        _lib.check(self.ctx.lib.ofb_pyramid(self.ctx.h, _lib.ptr(a), w, h, w, w * h, n, int(max_level), C.byref(hdl)))
+        if bgr:
+            _lib.check(self.ctx.lib.ofb_pyramid_bgr(self.ctx.h, _lib.ptr(a), w, h, 3 * w, 3 * w * h, n, int(max_level), C.byref(hdl)))
+        else:
+            _lib.check(self.ctx.lib.ofb_pyramid(self.ctx.h, _lib.ptr(a), w, h, w, w * h, n, int(max_level), C.byref(hdl)))
         self.h = hdl
         ni, nl = C.c_int(), C.c_int()
         ws = (C.c_int * 16)(); hs = (C.c_int * 16)(); ps = (C.c_int * 16)()

@@ -81,6 +81,10 @@ int ofb_bgr2gray(ofb_ctx* ctx, const uint8_t* bgr, int w, int h, int pitch, uint
  *      ((w+1)/2^l...) as in OpenCV. The pyramid is owned by the context until ofb_pyr_free. */
 int ofb_pyramid(ofb_ctx* ctx, const uint8_t* img, int w, int h, int pitch, size_t image_stride,
                 int n_images, int max_level, ofb_pyr** out);
+/* The same from BGR8 frames (3 bytes per pixel, pitch >= 3*w): cv2.cvtColor(BGR2GRAY) fused into the first pyramid step --
+ * one kernel reads the BGR frame, writes the grey level 0 and level 1 (velocity_measurment_node:113 + :133). */
+int ofb_pyramid_bgr(ofb_ctx* ctx, const uint8_t* bgr, int w, int h, int pitch, size_t image_stride,
+                    int n_images, int max_level, ofb_pyr** out);
 int ofb_pyr_free(ofb_ctx* ctx, ofb_pyr* pyr);
 int ofb_pyr_info(const ofb_pyr* pyr, int* n_images, int* n_levels, int* widths, int* heights, int* pitches);
 /* copy level `level` of image `image` to dst (host or device), dst_pitch bytes per row */
@@ -331,6 +335,14 @@ int ofb_mc_sweep(ofb_ctx* ctx, const ofb_mc_step* steps, int n_steps, int step_i
                  const double* pos, const double* true_flow, int total_points,
                  uint64_t trial_begin, uint64_t trials, uint64_t seed, int precision,
                  ofb_mc_sums* sums_out, double* v_dump, double* R_dump);
+
+/* The same sweep over SEVERAL contexts of this process (any mix of devices): contiguous trial shards, all enqueued
+ * before the first is waited for, sums merged on the host in context order. pos, true_flow and sums_out are host
+ * memory. The union of trials equals the one-context run (counter RNG); no torch, no NCCL. */
+int ofb_mc_sweep_multi(ofb_ctx** ctxs, int n_ctx, const ofb_mc_step* steps, int n_steps, int step_id_base,
+                       const double* pos, const double* true_flow, int total_points,
+                       uint64_t trial_begin, uint64_t trials, uint64_t seed, int precision,
+                       ofb_mc_sums* sums_out);
 
 /* feas_simulation: per-point sums over trials of the six quantities returned at
  * simulation.py:104 (backward par, backward dist, forward par, forward dist, backward res,

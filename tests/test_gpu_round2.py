@@ -254,3 +254,87 @@ def test_batched_solve_rejects_bad_offsets(ctx):
     rc = lib.ofb_solve_velocity_batched(ctx.h, 0, ofb200._lib.ptr(x), ofb200._lib.ptr(u), ofb200._lib.ptr(offs), 3, ofb200._lib.ptr(d),
                                         ofb200._lib.ptr(n3), ofb200._lib.ptr(w3), None, ofb200._lib.ptr(v), None, None, None)
     assert rc == ofb200._lib.OFB_E_INVALID and b"non-decreasing" in lib.ofb_last_error()
+
+
+def test_mc_sweep_over_several_contexts_of_one_process(ctx, points200):
+    """ofb_mc_sweep_multi: the library shards the trial range over the contexts it is given and merges the sums itself
+    (no torch.distributed). Two contexts on one device, and -- where the box has them -- one context per device, must
+    reproduce the one-context sums up to fp64 summation order; uneven and tiny trial counts included."""
+    import torch
+    import ofb200
+    sim = ofb200.simulation
+    steps, pos, flow = sim.build_sweep("flow_errors", points200[:50], k=7)
+    extra = [ofb200.Context(0), ofb200.Context(0)]
+    if torch.cuda.device_count() >= 2:
+        extra.append(ofb200.Context(1))
+    try:
+        for trials in (1, 2, 1001, 40_000):
+            whole = sim.run_steps(steps, pos, flow, trials, seed=5, trial_begin=77, ctx=ctx)
+            for group in ([ctx], [ctx, extra[0]], [ctx] + extra):
+                got = sim.run_steps_multi(steps, pos, flow, trials, group, seed=5, trial_begin=77)
+                assert np.array_equal(got["n"], whole["n"])
+                np.testing.assert_allclose(got.view(np.float64), whole.view(np.float64), rtol=1e-10, atol=1e-9)
+        again = sim.run_steps_multi(steps, pos, flow, 40_000, [ctx] + extra, seed=5, trial_begin=77)
+        assert np.array_equal(again.view(np.float64), got.view(np.float64))          # fixed merge order: bit-reproducible
+    finally:
+        for c in extra:
+            c.close()
+
+
+@pytest.mark.parametrize("shape", [(4, 4), (5, 7), (33, 37), (64, 128), (67, 131), (240, 320), (241, 323), (480, 640), (720, 1280)])
+def test_bgr_fused_pyramid_is_bit_exact(ctx, shape):
+    """ofb_pyramid_bgr: grey level 0 = cv2's BGR2GRAY rule (oracle), every level = pyrDown of the one below, for tile-
+    aligned, odd, tiny and multi-image inputs, unaligned row pitches included (widths that are not multiples of 16)."""
+    import ofb200
+    from oracle import image_oracle as io
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    frames = rng.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
+    frames[1, :, :, :] = rng.integers(0, 256, shape + (1,), dtype=np.uint8)          # a grey-valued colour frame
+    p = ofb200.Pyramid(frames, 4, ctx=ctx, bgr=True)
+    try:
+        for i in range(3):
+            ref = io.build_pyramid(io.bgr2gray(frames[i]), p.n_levels - 1)
+            for l in range(p.n_levels):
+                got = p.level(l, i)
+                assert got.shape == ref[l].shape and np.array_equal(got, ref[l]), (shape, i, l, np.argwhere(got != ref[l])[:4])
+    finally:
+        p.close()
+    p0 = ofb200.Pyramid(frames[0], 0, ctx=ctx, bgr=True)            # no level 1: plain conversion path
+    assert np.array_equal(p0.level(0), io.bgr2gray(frames[0]))
+    p0.close()
+
+
+def test_tracker_bgr_fused_equals_separate_conversion(ctx):
+    """The lifecycle on BGR frames: fused conversion + first pyramid step vs the separate conversion kernel
+    (OFB_BGR_FUSED=0) vs grey frames converted beforehand -- identical records, points and velocities."""
+    import ofb200
+    h, w = 240, 320
+    a, b, mo = synth.make_pair(h, w, 4, 11, max_disp=4.0)
+    rng = np.random.default_rng(3)
+    tint = rng.integers(0, 40, (h, w, 3), dtype=np.uint8)
+    to_bgr = lambda g: np.clip(np.stack([g, g, g], -1).astype(np.int32) + tint - 20, 0, 255).astype(np.uint8)
+    A, B = to_bgr(a), to_bgr(b)
+    from oracle import image_oracle as io
+    ga, gb = io.bgr2gray(A), io.bgr2gray(B)
+    imu = np.zeros(1, ofb200._lib.IMU_DTYPE)
+    imu["d"], imu["n"], imu["w"] = mo["d"], mo["n"], mo["w"]
+    kw = dict(max_features=120, min_features=118, topup="node", mask_radius=12, variant="node", principal=(mo["cx"], mo["cy"]),
+              scaling=1.0 / mo["f"], flow_scaling=1.0 / (mo["f"] * mo["dt"]), ctx=ctx)
+
+    def run(frames, bgr, env=None):
+        if env is not None:
+            os.environ["OFB_BGR_FUSED"] = env
+        try:
+            trk = ofb200.StreamTracker(w, h, bgr=bgr, **kw)
+            out = [trk.step(f, imu, want_points=True) for f in frames]
+            trk.close()
+            return out
+        finally:
+            os.environ.pop("OFB_BGR_FUSED", None)
+    fused = run([A, B, A, B], True)
+    separate = run([A, B, A, B], True, env="0")
+    grey = run([ga, gb, ga, gb], False)
+    for x, y, z in zip(fused, separate, grey):
+        for f in ("v", "n_tracked", "n_kept", "n_added", "n_points", "flags"):
+            assert np.array_equal(x[0][f], y[0][f]) and np.array_equal(x[0][f], z[0][f]), f
+        assert np.array_equal(x[1][0], y[1][0]) and np.array_equal(x[1][0], z[1][0])
