@@ -242,3 +242,39 @@ def test_fleet_tracker_single_process():
     t = fleet.gather_velocities()
     assert t[0].tolist() == [0.0, 1.0, -1.0] and np.isnan(t[1]).all() and t[2].tolist() == [2.0, 1.0, -1.0]
     fleet.close()
+
+
+def _fleet_edge_worker(rank, world, port, q):
+    """a fleet with fewer streams than ranks (rank 1 owns nothing) and a gather before the first step"""
+    import torch.distributed as dist
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import ofb200
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    fleet = ofb200.FleetTracker(1, 64, 48, tracker_factory=lambda n, **kw: _FakeTracker(ofb200.simulation.stream_shard(1, rank, world)))
+    before = fleet.gather_velocities()            # nothing stepped yet: every row NaN, on every rank
+    fleet.step(None, None)
+    after = fleet.gather_velocities()
+    q.put((rank, fleet.streams, fleet.local is None, before.tolist(), after.tolist()))
+    fleet.close()
+    dist.destroy_process_group()
+
+
+def test_fleet_tracker_rank_without_streams_and_gather_before_first_step_gloo():
+    """a rank that owns no stream still takes part in the (single) all-reduce, and rows of streams that have
+    not solved yet are NaN, not zeros."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fleet_edge_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert outs[0][1] == [0] and outs[1][1] == [] and outs[1][2] is True
+    for _, _, _, before, after in outs:
+        assert np.isnan(np.array(before)).all() and np.array(before).shape == (1, 3)
+        assert np.array(after).tolist() == [[0.0, 1.0, -1.0]]
