@@ -190,7 +190,8 @@ enum {
     FS_CAND = 12,            // + write_map                              (2 slots)
     FS_SELECT = 14,          // + {256, 512, 1024 threads}               (3 slots)
     FS_LK = 17,
-    FS_PYR_TOP = 18
+    FS_PYR_TOP = 18,
+    FS_SELECT16 = 19         // + {256, 512, 1024 threads}: non-portable cluster size (16) allowed     (3 slots)
 };
 // Raises a kernel's dynamic shared-memory limit on the context's device when this context has not done so yet.
 template <class F>
