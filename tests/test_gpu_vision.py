@@ -415,7 +415,13 @@ def test_selection_cluster_mode_equals_single_cta(ctx):
     cases = [(synth.texture(240, 320, 61), dict(maxCorners=200, qualityLevel=0.01, minDistance=10, blockSize=7)),
              (synth.texture(480, 640, 62), dict(maxCorners=0, qualityLevel=0.001, minDistance=2, blockSize=3)),
              (synth.texture(300, 500, 63), dict(maxCorners=5000, qualityLevel=0.01, minDistance=0, blockSize=7)),
-             (synth.texture(131, 517, 64), dict(maxCorners=60, qualityLevel=0.3, minDistance=20, blockSize=12))]
+             (synth.texture(131, 517, 64), dict(maxCorners=60, qualityLevel=0.3, minDistance=20, blockSize=12)),
+             # a tiled image: every interior corner value occurs 80 times, so chunk boundaries fall inside plateaus of equal
+             # lambda_min (the routed preparation must fall back or split the plateau by address exactly)
+             (np.ascontiguousarray(np.tile(synth.texture(32, 32, 65), (8, 10))),
+              dict(maxCorners=3000, qualityLevel=0.01, minDistance=3, blockSize=5)),
+             (np.ascontiguousarray(np.tile(synth.texture(16, 16, 66), (30, 40))),
+              dict(maxCorners=0, qualityLevel=0.05, minDistance=1, blockSize=3))]
     for img, kw in cases:
         os.environ["OFB_SELECT_CLUSTER"] = "1"
         try:
