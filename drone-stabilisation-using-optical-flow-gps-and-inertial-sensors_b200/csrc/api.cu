@@ -86,6 +86,7 @@ extern "C" int ofb_ctx_destroy(ofb_ctx* ctx)
 extern "C" int ofb_ctx_sync(ofb_ctx* ctx)
 {
     OFB_REQUIRE(ctx, "ctx_sync: null context");
+    OFB_CUDA(ofb_join_aux(ctx));
     OFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return OFB_OK;
 }
@@ -94,6 +95,7 @@ extern "C" int ofb_ctx_stream(ofb_ctx* ctx, void** cuda_stream_out)
 {
     OFB_REQUIRE(ctx && cuda_stream_out, "ctx_stream: null argument");
     *cuda_stream_out = (void*)ctx->stream;
+    ctx->stream_exported = true;
     return OFB_OK;
 }
 
@@ -114,6 +116,7 @@ extern "C" int ofb_timer_start(ofb_ctx* ctx)
 extern "C" int ofb_timer_stop(ofb_ctx* ctx, float* ms_out)
 {
     OFB_REQUIRE(ctx && ms_out, "timer_stop: null argument");
+    OFB_CUDA(ofb_join_aux(ctx));
     OFB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     OFB_CUDA(cudaEventSynchronize(ctx->ev1));
     OFB_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
@@ -150,7 +153,9 @@ extern "C" int ofb_host_free_pinned(ofb_ctx* ctx, void* p)
 extern "C" int ofb_memcpy_async(ofb_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     OFB_REQUIRE(ctx && dst && src, "memcpy: null argument");
+    OFB_CUDA(ofb_join_aux(ctx));
     OFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    if (ofb_is_device_ptr(dst)) ctx->async_writes++;
     return OFB_OK;
 }
 extern "C" int ofb_memcpy(ofb_ctx* ctx, void* dst, const void* src, size_t bytes)

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <vector>
+#include <utility>
 #include "../../include/ofb200.h"
 
 void ofb_set_error(const char* fmt, ...);
@@ -78,6 +79,15 @@ struct ofb_ctx {
     bool own_stream = false;
     int sm_count = 148;
     uint64_t launches = 0;
+    // what a caller may have put on the stream besides API calls that launch kernels: asynchronous copies into device memory
+    // (ofb_memcpy_async) and anything at all once the stream handle was handed out (ofb_ctx_stream). The tracker moves its
+    // ingest to an internal stream only when neither happened since its previous step (see tracker_step_launches).
+    const int* lk_lo = nullptr;         // set around an ofb_lk_device call: per-pair first feature to track (LKParams::counts_lo)
+    // streams of objects living on this context (a tracker's deferred top-up) that must be joined before the context's
+    // stream counts as "done": ofb_ctx_sync, ofb_timer_stop and the memcpy calls wait for them (ofb_join_aux)
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> aux_join;
+    uint64_t async_writes = 0;
+    bool stream_exported = false;
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: what this context has already
     // requested for each kernel that needs more than 48 KB (slot = FS_* below). Per context, hence per device.
     size_t func_smem[OFB_NFUNC_SLOTS] = {};
@@ -130,6 +140,17 @@ struct ofb_pyr {
     bool level0_owned = false;
     size_t bytes = 0;
 };
+
+// order the context's stream behind everything enqueued on the registered auxiliary streams
+static inline cudaError_t ofb_join_aux(ofb_ctx* ctx)
+{
+    for (auto& sj : ctx->aux_join) {
+        cudaError_t e = cudaEventRecord(sj.second, sj.first);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, sj.second, 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 static inline bool ofb_is_device_ptr(const void* p)
 {

@@ -76,6 +76,7 @@ lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restric
     int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
     int feat = blockIdx.x * LK_WARPS + warp;
     if (feat >= n) return;
+    if (P.counts_lo && feat < P.counts_lo[(size_t)pair * counts_stride]) return;
     const int winW = P.win_w, winH = P.win_h, npx = winW * winH;
     const int RW = winW + 3, RH = winH + 3, RP = (RW + 3) & ~3;
     const int DW = winW + 1, DH = winH + 1;
@@ -317,6 +318,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
     const int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
     const int feat = blockIdx.x * LKF_WARPS + (threadIdx.x >> 5);
     if (feat >= n) return;
+    if (P.counts_lo && feat < P.counts_lo[(size_t)pair * counts_stride]) return;
     const int winW = P.win_w, winH = P.win_h;
     const int r = lane >> 1, hh = lane & 1;
     const size_t po = (size_t)pair * pts_stride + feat;
@@ -516,6 +518,7 @@ lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restric
     const int n = counts ? counts[(size_t)pair * counts_stride] : n_uniform;
     const int feat = blockIdx.x * LKF_WARPS + (threadIdx.x >> 5);
     if (feat >= n) return;
+    if (P.counts_lo && feat < P.counts_lo[(size_t)pair * counts_stride]) return;
     const int winW = P.win_w, winH = P.win_h;
     const int r = lane >> 1, hh = lane & 1;
     const size_t po = (size_t)pair * pts_stride + feat;
@@ -753,6 +756,7 @@ int ofb_lk_device(ofb_ctx* ctx, const ofb_pyr* prev, int prev_image0, int prev_s
         eff = l + 1;
     }
     P.nlev = eff;
+    P.counts_lo = ctx->lk_lo;
     fill_levels(&P.prev, prev);
     fill_levels(&P.next, next);
     for (int l = 0; l < eff; ++l) {

@@ -25,6 +25,7 @@ struct LKParams {
     float eps_lo, eps_hi;         // fp32 brackets of eps: |delta|^2 below eps_lo / above eps_hi decides without fp64
     float hwx, hwy;               // (win - 1) / 2
     int prev_image0, prev_image_step, next_image0, next_image_step;   // image of pair p = image0 + p*step
+    const int* counts_lo;         // optional: features below counts_lo[pair * counts_stride] are skipped (ofb_ctx::lk_lo)
 };
 
 // Device-pointer core. counts (optional): per-pair feature count at counts[pair*counts_stride];

@@ -32,7 +32,7 @@ struct ofb_tracker {
     bool have_prev = false;
     DevBuf pts[2];                     // float2 [S][cap]; pts[pcur] = current point sets
     int pcur = 0;
-    DevBuf counts;                     // int [3][S]: count, need (top-up flag), kept (count after the gates)
+    DevBuf counts;                     // int [4][S]: count, need (top-up flag), kept (count after the gates), count0 (before the top-up)
     DevBuf nxt, status, err, kept_prev, det, vlast, mask, hw, bgr;
     // CUDA-graph replay of the steady-state step for small fleets fed from host memory (the launch-bound case: a
     // step is ~15 tiny launches/copies). Inputs are staged in pinned buffers at fixed addresses, so one captured
@@ -46,16 +46,31 @@ struct ofb_tracker {
     bool cond_ok = true;               // the top-up path may sit in a conditional (IF) node of the graph (opt-in)
     bool capturing = false, capture_cond = false, cond_used = false;
     cudaStream_t side_stream = nullptr;   // captures the body of the conditional node
+    // the new frame's ingest + pyramid run on their own stream: they only have to wait for the LK of the previous step (it
+    // read the pyramid slot that is overwritten), so they overlap the previous step's filter / solve / top-up kernels
+    cudaStream_t pyr_stream = nullptr;
+    cudaEvent_t ev_lk = nullptr, ev_pyr = nullptr;
+    bool lk_recorded = false;          // ev_lk marks the LK launch of the previous step
+    uint64_t launches_end = ~0ull, async_end = 0;   // the context's counters when the previous step returned
+    // deferred top-up: with device-resident results and no point read-back the top-up path (mask, lambda_min, selection,
+    // append: four launches that exit at once on most frames) runs in a child context -- own stream, own detector
+    // scratch -- and the NEXT step tracks the surviving points (they do not depend on it) before it joins and tracks
+    // what the top-up appended. The parent context's sync / timer / memcpy calls join the child stream (aux_join).
+    ofb_ctx* top_ctx = nullptr;
+    cudaEvent_t ev_filter = nullptr, ev_top = nullptr, ev_join = nullptr;
+    bool top_pending = false;          // a deferred top-up has not been joined into the context's stream yet
     int plain_steps = 0;               // steps run launch by launch since creation (scratch arenas are sized by them)
     uint64_t graph_steps = 0;
 };
+
+static cudaError_t tracker_join_topup(ofb_tracker* t);
 
 namespace {
 
 struct TrackerDev {
     const float* prev; const float* next; const uint8_t* status;   // [S][cap] LK input / output
     float* kept_prev; float* kept_next;                             // [S][cap] compacted
-    int* count; int* need; int* kept;
+    int* count; int* need; int* kept; int* count0;
     double* vlast;                                                  // [S][3]
     int cap;
     int variant; double cx, cy, ps, fs;
@@ -189,6 +204,7 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         T.kept[s] = kept;
         T.need[s] = need;
         T.count[s] = (need && T.topup_mode == OFB_TOPUP_REPLACE) ? 0 : kept;    // of_module.py:86 replaces the set
+        T.count0[s] = T.count[s];                                                // (the top-up appends behind this)
     }
 }
 
@@ -349,7 +365,7 @@ extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_
     R(t->pts[0], sizeof(float) * 2 * np); R(t->pts[1], sizeof(float) * 2 * np);
     R(t->nxt, sizeof(float) * 2 * np); R(t->kept_prev, sizeof(float) * 2 * np);
     R(t->status, np); R(t->err, sizeof(float) * np);
-    R(t->counts, sizeof(int) * 3 * S); R(t->det, sizeof(float) * 2 * (size_t)S * K);
+    R(t->counts, sizeof(int) * 4 * S); R(t->det, sizeof(float) * 2 * (size_t)S * K);
     R(t->vlast, sizeof(double) * 3 * S);
     if (cfg->topup_mode == OFB_TOPUP_APPEND_MASKED && cfg->mask_radius > 0) {
         R(t->mask, t->stride_d * S);
@@ -363,7 +379,7 @@ extern "C" int ofb_tracker_create(ofb_ctx* ctx, const ofb_tracker_cfg* cfg, ofb_
         ce = cudaMemcpyAsync(t->hw.p, hw.data(), sizeof(int) * hw.size(), cudaMemcpyHostToDevice, ctx->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);      // hw is a local
     }
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * S, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 4 * S, ctx->stream);
     if (ce == cudaSuccess) ce = tracker_seed_prior(t);
     if (ce != cudaSuccess) {
         ofb_set_error("tracker_create: %s", cudaGetErrorString(ce));
@@ -386,6 +402,20 @@ extern "C" int ofb_tracker_destroy(ofb_tracker* t)
         for (int j = 0; j < 2; ++j) if (t->gexec[i][j]) cudaGraphExecDestroy(t->gexec[i][j]);
     t->pin_in.release(); t->pin_out.release();
     if (t->side_stream) cudaStreamDestroy(t->side_stream);
+    if (t->pyr_stream) { cudaStreamSynchronize(t->pyr_stream); cudaStreamDestroy(t->pyr_stream); }
+    if (t->top_ctx) {
+        cudaStreamSynchronize(t->top_ctx->stream);
+        if (t->ctx)
+            for (size_t i = 0; i < t->ctx->aux_join.size(); ++i)
+                if (t->ctx->aux_join[i].first == t->top_ctx->stream) { t->ctx->aux_join.erase(t->ctx->aux_join.begin() + i); break; }
+        ofb_ctx_destroy(t->top_ctx);
+        if (t->ctx) cudaSetDevice(t->ctx->device);
+    }
+    if (t->ev_filter) cudaEventDestroy(t->ev_filter);
+    if (t->ev_top) cudaEventDestroy(t->ev_top);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->ev_lk) cudaEventDestroy(t->ev_lk);
+    if (t->ev_pyr) cudaEventDestroy(t->ev_pyr);
     DevBuf* bufs[] = {&t->counts, &t->nxt, &t->status, &t->err, &t->kept_prev, &t->det, &t->vlast, &t->mask, &t->hw, &t->bgr, &t->dev_io};
     for (DevBuf* b : bufs) b->release();
     delete t;
@@ -397,7 +427,9 @@ extern "C" int ofb_tracker_reset(ofb_tracker* t)
     OFB_REQUIRE(t, "tracker_reset: null tracker");
     OFB_CUDA(cudaSetDevice(t->ctx->device));
     t->have_prev = false;
-    OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 3 * t->cfg.n_streams, t->ctx->stream));
+    t->lk_recorded = false;
+    OFB_CUDA(tracker_join_topup(t));
+    OFB_CUDA(cudaMemsetAsync(t->counts.p, 0, sizeof(int) * 4 * t->cfg.n_streams, t->ctx->stream));
     OFB_CUDA(tracker_seed_prior(t));
     return OFB_OK;
 }
@@ -414,6 +446,7 @@ extern "C" int ofb_tracker_set_points(ofb_tracker* t, const float* pts, const in
     OFB_REQUIRE(t && pts && counts, "tracker_set_points: null argument");
     ofb_ctx* ctx = t->ctx;
     OFB_CUDA(cudaSetDevice(ctx->device));
+    OFB_CUDA(tracker_join_topup(t));
     const int S = t->cfg.n_streams;
     if (!ofb_is_device_ptr(counts))
         for (int s = 0; s < S; ++s)
@@ -422,6 +455,14 @@ extern "C" int ofb_tracker_set_points(ofb_tracker* t, const float* pts, const in
     OFB_CUDA(cudaMemcpyAsync(t->counts.p, counts, sizeof(int) * S, cudaMemcpyDefault, ctx->stream));
     OFB_CUDA(cudaStreamSynchronize(ctx->stream));                     // the caller's buffers are free on return
     return OFB_OK;
+}
+
+// order the context's stream behind a deferred top-up that is still pending (see ofb_tracker::top_ctx)
+static cudaError_t tracker_join_topup(ofb_tracker* t)
+{
+    if (!t->top_pending) return cudaSuccess;
+    t->top_pending = false;
+    return cudaStreamWaitEvent(t->ctx->stream, t->ev_top, 0);
 }
 
 // One step, launch by launch, on ctx->stream (also the body that is captured into a graph).
@@ -446,6 +487,49 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     uint8_t* fown = t->frames[t->cur].as<uint8_t>();
     int fpitch = t->pitch_d; size_t fstride = t->stride_d;
     bool fused_bgr = false; const uint8_t* bgr_src = nullptr; int bgr_pitch = 0; size_t bgr_stride = 0;
+    // Ingest + pyramid go to their own stream (OFB_TRACKER_EARLY_PYR=0: everything on the context's stream): the slot they
+    // write was last read by the previous step's LK, nothing else of that step touches it, so they overlap the previous
+    // step's filter / solve / top-up. Not while a graph is captured (the graph is for the launch-bound host-fed case),
+    // not in profile mode (stage events live on one stream), and never on a stream the caller owns or has been handed
+    // (work enqueued there must stay ordered in front of this step). On the context's own stream other API calls may
+    // have produced this frame since the previous step (a kernel launch, an asynchronous copy into device memory): the
+    // ingest is then ordered behind everything enqueued so far, which costs the overlap for this step only.
+    cudaStream_t const main_stream0 = ctx->stream;
+    bool early = false;
+    {
+        const char* ee = getenv("OFB_TRACKER_EARLY_PYR");
+        early = !t->capturing && !ctx->profile && ctx->own_stream && !ctx->stream_exported && !(ee && ee[0] == '0');
+    }
+    if (ctx->launches != t->launches_end || ctx->async_writes != t->async_end) t->lk_recorded = false;
+    // deferred top-up (opt-in, OFB_TRACKER_DEFER_TOPUP=1): only when nothing of this call is read back on the host and no
+    // output of the call depends on the top-up except the device-resident result records. Measured on B200 (one stream,
+    // device frames, asynchronous calls): it shortens the GPU chain of a 1080p step from 50.7 to <= 45 us, but the second
+    // LK launch and four more event operations raise the host's enqueue time from 30 to 45 us per step -- a 1080p
+    // stream gains 11 %, a 640x480 stream (host bound) loses 20 %, a 256-stream fleet loses 2.5 %: off by default.
+    bool defer = false;
+    {
+        const char* de = getenv("OFB_TRACKER_DEFER_TOPUP");
+        defer = early && ofb_is_device_ptr(results) && !pts_out && !n_out && de && de[0] == '1';
+    }
+    if (defer && !t->top_ctx) {
+        OFB_TRY(ofb_ctx_create(ctx->device, &t->top_ctx));
+        OFB_CUDA(cudaEventCreateWithFlags(&t->ev_filter, cudaEventDisableTiming));
+        OFB_CUDA(cudaEventCreateWithFlags(&t->ev_top, cudaEventDisableTiming));
+        OFB_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+        ctx->aux_join.push_back(std::make_pair(t->top_ctx->stream, t->ev_join));
+    }
+    ofb_ctx* const fctx = defer ? t->top_ctx : ctx;                   // the context the top-up path runs in
+    if (early) {
+        if (!t->pyr_stream) {
+            OFB_CUDA(cudaStreamCreateWithFlags(&t->pyr_stream, cudaStreamNonBlocking));
+            OFB_CUDA(cudaEventCreateWithFlags(&t->ev_lk, cudaEventDisableTiming));
+            OFB_CUDA(cudaEventCreateWithFlags(&t->ev_pyr, cudaEventDisableTiming));
+        }
+        if (!t->lk_recorded) OFB_CUDA(cudaEventRecord(t->ev_lk, main_stream0));   // no LK to wait for: behind all earlier work
+        OFB_CUDA(cudaStreamWaitEvent(t->pyr_stream, t->ev_lk, 0));
+        ctx->stream = t->pyr_stream;
+    }
+    const int ingest_rc = [&]() -> int {
     if (cfg.bgr_input) {
         const uint8_t* src = frames; int spitch = pitch; size_t sstride = image_stride;
         if (!ofb_is_device_ptr(frames)) {
@@ -478,6 +562,14 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     }
     OFB_TRY(ofb_pyr_prepare(ctx, &t->pyr[t->cur], f, w, h, fpitch, fstride, S, S, pc.max_level, !fused_bgr));
     if (fused_bgr) OFB_TRY(ofb_pyr_ingest_bgr(ctx, t->pyr[t->cur], bgr_src, bgr_pitch, bgr_stride));
+    return OFB_OK;
+    }();
+    ctx->stream = main_stream0;
+    if (ingest_rc != OFB_OK) return ingest_rc;
+    if (early) {
+        OFB_CUDA(cudaEventRecord(t->ev_pyr, t->pyr_stream));
+        OFB_CUDA(cudaStreamWaitEvent(main_stream0, t->ev_pyr, 0));
+    }
     int* count = t->counts.as<int>();
     int* need = count + S;
     int* keptn = count + 2 * S;
@@ -486,12 +578,12 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     TrackerDev T;
     T.prev = P; T.next = t->nxt.as<float>(); T.status = t->status.as<uint8_t>();
     T.kept_prev = t->kept_prev.as<float>(); T.kept_next = Pn;
-    T.count = count; T.need = need; T.kept = keptn; T.vlast = t->vlast.as<double>();
+    T.count = count; T.need = need; T.kept = keptn; T.count0 = count + 3 * S; T.vlast = t->vlast.as<double>();
     T.cap = cap; T.variant = pc.variant; T.cx = pc.cx; T.cy = pc.cy; T.ps = pc.pos_scale; T.fs = pc.flow_scale;
     T.max_speed = cfg.max_speed; T.dummy = cfg.dummy_value; T.gate_mode = cfg.gate_mode; T.gate_T = cfg.gate_T;
     T.min_solve = cfg.min_solve; T.min_features = cfg.min_features; T.topup_mode = cfg.topup_mode; T.max_features = K;
     T.have_prev = t->have_prev ? 1 : 0;
-    OFB_TRY(ofb_features_scratch(ctx, w, h, pc.min_distance, S, &T.feat_state, &T.cell_grid, &T.cell_stride));
+    OFB_TRY(ofb_features_scratch(fctx, w, h, pc.min_distance, S, &T.feat_state, &T.cell_grid, &T.cell_stride));
     // graph capture: the top-up path goes into the body of an IF node whose condition the filter kernel sets, so a
     // steady-state replay does not even launch the five kernels and two memsets that would exit at once
     T.use_cond = 0; T.cond = 0;
@@ -507,10 +599,26 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
         T.use_cond = 1;
     }
     // 2. track the stream's points from the kept frame into the new one
-    if (t->have_prev)
-        OFB_TRY(ofb_lk_device(ctx, t->pyr[t->cur ^ 1], 0, 1, t->pyr[t->cur], 0, 1, S, P, count, 1, cap, (size_t)cap, pc.win_w,
-                              pc.win_h, pc.max_level, pc.max_count, pc.eps, 0, pc.min_eig_thr, t->nxt.as<float>(),
-                              t->status.as<uint8_t>(), t->err.as<float>()));
+    auto lk = [&](const int* hi, const int* lo) -> int {
+        ctx->lk_lo = lo;
+        const int rc = ofb_lk_device(ctx, t->pyr[t->cur ^ 1], 0, 1, t->pyr[t->cur], 0, 1, S, P, hi, 1, cap, (size_t)cap, pc.win_w,
+                                     pc.win_h, pc.max_level, pc.max_count, pc.eps, 0, pc.min_eig_thr, t->nxt.as<float>(),
+                                     t->status.as<uint8_t>(), t->err.as<float>());
+        ctx->lk_lo = nullptr;
+        return rc;
+    };
+    if (t->have_prev && t->top_pending && early) {
+        // the previous step's top-up may still be running in the child context: the points that survived that step are
+        // tracked now, what the top-up appended (positions count0 .. count) once it has finished
+        OFB_TRY(lk(T.count0, nullptr));
+        OFB_CUDA(tracker_join_topup(t));
+        OFB_TRY(lk(count, T.count0));
+    } else {
+        OFB_CUDA(tracker_join_topup(t));
+        if (t->have_prev) OFB_TRY(lk(count, nullptr));
+    }
+    t->lk_recorded = false;
+    if (early && t->have_prev) { OFB_CUDA(cudaEventRecord(t->ev_lk, ctx->stream)); t->lk_recorded = true; }
     // 3.+4. status filter, gates, solve; the compacted new positions become the point set (Pn)
     track_filter_solve_kernel<<<S, OFB_SOLVE_THREADS, 0, ctx->stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
                                                                         (ofb_track_result*)o[0].dev);
@@ -526,6 +634,11 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     OFB_TRY(copy_out(kept_next, Pn));                                 // the head of the new point set, before any top-up
     // 5. top-up on the current frame; streams that do not need it are skipped inside the kernels (no host sync)
     cudaStream_t main_stream = ctx->stream;
+    const uint64_t top_l0 = fctx->launches;
+    if (defer) {
+        OFB_CUDA(cudaEventRecord(t->ev_filter, main_stream));
+        OFB_CUDA(cudaStreamWaitEvent(fctx->stream, t->ev_filter, 0));
+    }
     cudaGraphNode_t cond_node = nullptr;
     if (T.use_cond) {
         cudaStreamCaptureStatus cs; const cudaGraphNode_t* deps = nullptr; size_t nd = 0;
@@ -556,22 +669,27 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     };
     const uint8_t* mask = nullptr;
     if (cfg.topup_mode == OFB_TOPUP_APPEND_MASKED && cfg.mask_radius > 0) {
-        const int mr = render_mask_device(ctx, t->mask.as<uint8_t>(), w, h, t->pitch_d, t->stride_d, S, Pn, (size_t)cap, cap, count,
+        const int mr = render_mask_device(fctx, t->mask.as<uint8_t>(), w, h, t->pitch_d, t->stride_d, S, Pn, (size_t)cap, cap, count,
                                           need, t->hw.as<int>(), cfg.mask_radius);
         if (mr != OFB_OK) return end_body(mr);
         mask = t->mask.as<uint8_t>();
     }
     FeatImageState* st = nullptr;
     const unsigned int cand_cap = (unsigned int)(((size_t)w * h) / 4 + 1024);
-    ctx->feat_active = need;
-    ctx->feat_prezeroed = true;                                       // done by track_filter_solve_kernel
-    int fr = ofb_features_device(ctx, f, w, h, fpitch, (S == 1 ? 0 : fstride), S, mask, t->pitch_d, t->stride_d, K, pc.quality,
+    fctx->feat_active = need;
+    fctx->feat_prezeroed = true;                                      // done by track_filter_solve_kernel
+    int fr = ofb_features_device(fctx, f, w, h, fpitch, (S == 1 ? 0 : fstride), S, mask, t->pitch_d, t->stride_d, K, pc.quality,
                                  pc.min_distance, pc.block_size, cand_cap, t->det.as<float>(), (size_t)2 * K, K, &st);
-    ctx->feat_active = nullptr;
-    ctx->feat_prezeroed = false;
+    fctx->feat_active = nullptr;
+    fctx->feat_prezeroed = false;
     if (fr != OFB_OK) return end_body(fr);
-    topup_append_kernel<<<S, 128, 0, ctx->stream>>>(T, st, t->det.as<float>(), Pn, (ofb_track_result*)o[0].dev);
-    ctx->launches++;
+    topup_append_kernel<<<S, 128, 0, fctx->stream>>>(T, st, t->det.as<float>(), Pn, (ofb_track_result*)o[0].dev);
+    fctx->launches++;
+    if (defer) {
+        OFB_CUDA(cudaEventRecord(t->ev_top, fctx->stream));
+        t->top_pending = true;
+        ctx->launches += fctx->launches - top_l0;                     // (bench.py's gpu_launches reads the parent's counter)
+    }
     {
         const cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { ofb_set_error("tracker_step: topup_append launch -> %s", cudaGetErrorString(le)); return end_body(OFB_E_CUDA); }
@@ -582,6 +700,7 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     t->pcur ^= 1;
     t->cur ^= 1;
     t->have_prev = true;
+    t->launches_end = ctx->launches; t->async_end = ctx->async_writes;
     int rc = ofb_finish_out(ctx, o, 2);
     if (rc == OFB_OK && host_out) OFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return rc;
@@ -666,7 +785,9 @@ static int tracker_step_graph(ofb_tracker* t, const uint8_t* frames, int pitch, 
         if (with_cond) t->cond_used = true;
     }
     if (!t->gexec[par][hp]) return OFB_E_UNSUPPORTED;
+    OFB_CUDA(tracker_join_topup(t));
     OFB_CUDA(cudaGraphLaunch(t->gexec[par][hp], ctx->stream));
+    t->lk_recorded = false;             // (a later launch-by-launch step orders its ingest behind this graph)
     ctx->launches += t->glaunches[par][hp];
     t->pcur ^= 1; t->cur ^= 1; t->graph_steps++;
     OFB_CUDA(cudaStreamSynchronize(ctx->stream));

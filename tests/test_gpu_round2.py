@@ -338,3 +338,59 @@ def test_tracker_bgr_fused_equals_separate_conversion(ctx):
         for f in ("v", "n_tracked", "n_kept", "n_added", "n_points", "flags"):
             assert np.array_equal(x[0][f], y[0][f]) and np.array_equal(x[0][f], z[0][f]), f
         assert np.array_equal(x[1][0], y[1][0]) and np.array_equal(x[1][0], z[1][0])
+
+
+def test_tracker_stream_overlap_modes_are_identical(ctx):
+    """ofb_tracker_step with device-resident frames / IMU / result records runs the ingest + pyramid on its own stream and
+    defers the top-up path to a child context (the next step tracks the surviving points before it joins). All of that is
+    scheduling only: the records of every step and the final point sets must equal the single-stream schedule
+    (OFB_TRACKER_EARLY_PYR=0), with frequent top-ups (min_features close to max_features), for one stream and a small fleet."""
+    import torch
+    import ofb200
+    P = ofb200._lib.ptr
+    h, w = 240, 320
+    for S in (1, 3):
+        seqs = []
+        for s in range(S):
+            a, b, mo = synth.make_pair(h, w, s, 5 + s, max_disp=5.0)
+            seqs.append((a, b, mo))
+        mo = seqs[0][2]
+        imu = np.zeros(S, ofb200._lib.IMU_DTYPE)
+        for s in range(S):
+            imu["d"][s], imu["n"][s], imu["w"][s] = seqs[s][2]["d"], seqs[s][2]["n"], seqs[s][2]["w"]
+        fa = torch.from_numpy(np.stack([q[0] for q in seqs])).cuda()
+        fb = torch.from_numpy(np.stack([q[1] for q in seqs])).cuda()
+        d_imu = torch.from_numpy(imu.view(np.uint8).reshape(-1).copy()).cuda()
+        nsteps = 9
+        rsz = ofb200._lib.TRACK_RESULT_DTYPE.itemsize
+        kw = dict(max_features=150, min_features=140, n_streams=S, topup="node", mask_radius=10, variant="node",
+                  principal=(mo["cx"], mo["cy"]), scaling=1.0 / mo["f"], flow_scaling=1.0 / (mo["f"] * mo["dt"]),
+                  borrow_frames=True, ctx=ctx)
+
+        def run(early, defer):
+            os.environ["OFB_TRACKER_EARLY_PYR"], os.environ["OFB_TRACKER_DEFER_TOPUP"] = early, defer
+            try:
+                trk = ofb200.StreamTracker(w, h, **kw)
+                d_res = torch.zeros(nsteps * S * rsz, dtype=torch.uint8, device="cuda")
+                for k in range(nsteps):
+                    f = fb if k & 1 else fa
+                    ofb200._lib.check(ctx.lib.ofb_tracker_step(trk.h, P(f), w, w * h, P(d_imu), None, d_res.data_ptr() + k * S * rsz,
+                                                               None, None, None, None))
+                # the last step through the host path: it must join whatever is still pending and return the point sets
+                last, pts = trk.step((fb if nsteps & 1 else fa), imu, want_points=True)
+                ctx.sync()
+                res = np.zeros(nsteps * S, ofb200._lib.TRACK_RESULT_DTYPE)
+                ctx.memcpy(res, d_res, res.nbytes)
+                trk.close()
+                return res, last, pts
+            finally:
+                os.environ.pop("OFB_TRACKER_EARLY_PYR", None); os.environ.pop("OFB_TRACKER_DEFER_TOPUP", None)
+        ref = run("0", "0")
+        assert ref[0]["n_added"].sum() > 0, "the case must exercise the top-up"
+        for early, defer in (("1", "0"), ("1", "1")):
+            got = run(early, defer)
+            for f in ("v", "n_prev", "n_tracked", "n_kept", "n_added", "n_points", "flags"):
+                assert np.array_equal(got[0][f], ref[0][f], equal_nan=True), (S, early, defer, f)
+                assert np.array_equal(got[1][f], ref[1][f], equal_nan=True), (S, early, defer, f, "last")
+            for s in range(S):
+                assert np.array_equal(got[2][s], ref[2][s]), (S, early, defer, s)

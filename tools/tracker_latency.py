@@ -2,10 +2,11 @@ import sys, time, numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import ofb200, synth
 ctx = ofb200.Context(0)
-w, h = 640, 480
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (640, 480)
+NF = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 a, b, mo = synth.make_pair(h, w, 0, 0)
 imu = np.zeros(1, ofb200._lib.IMU_DTYPE); imu["d"], imu["n"], imu["w"] = mo["d"], mo["n"], mo["w"]
-kw = dict(max_features=200, min_features=100, topup="node", mask_radius=30, variant="node", principal=(mo["cx"], mo["cy"]),
+kw = dict(max_features=NF, min_features=NF // 2, topup="node", mask_radius=30, variant="node", principal=(mo["cx"], mo["cy"]),
           scaling=1.0 / mo["f"], flow_scaling=1.0 / (mo["f"] * mo["dt"]), ctx=ctx)
 P = ofb200._lib.ptr
 da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
