@@ -74,6 +74,7 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
     T dn0 = P.nh[0] - P.n[0], dn1 = P.nh[1] - P.n[1], dn2 = P.nh[2] - P.n[2];
 
     T m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, g0 = 0, g1 = 0, g2 = 0, accR = 0;
+#pragma unroll 2
     for (int j = 0; j < P.N; ++j) {
         mc_normals4<T>(tlo, thi, 3u + (uint32_t)j, step, key, z0, z1, z2, z3);
         T dfx = P.sf * z0, dfy = P.sf * z1, dpx = P.sp * z2, dpy = P.sp * z3;

@@ -499,6 +499,9 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
     {
         const char* ee = getenv("OFB_TRACKER_EARLY_PYR");
         early = !t->capturing && !ctx->profile && ctx->own_stream && !ctx->stream_exported && !(ee && ee[0] == '0');
+        // a large grey fleet saturates the GPU by itself: there is no latency to hide and the second stream only costs
+        // (256 x 720p: 283 k -> 280 k pairs/s; the heavier BGR ingest still gains 2 %)
+        if (early && !cfg.bgr_input && (size_t)S * w * h > ((size_t)32 << 20) && !(ee && ee[0] == '1')) early = false;
     }
     if (ctx->launches != t->launches_end || ctx->async_writes != t->async_end) t->lk_recorded = false;
     // deferred top-up (opt-in, OFB_TRACKER_DEFER_TOPUP=1): only when nothing of this call is read back on the host and no
