@@ -25,9 +25,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    bdir = os.path.join(CSRC, "build")
+def build(force=False, verbose=False, debug=False):
+    """debug=True: libofb200_dbg.so with -DOFB_DEBUG_BOUNDS=1 (device-side index assertions, see csrc/common.cuh);
+    select it with OFB200_LIB=<path> when running the tests."""
+    bdir = os.path.join(CSRC, "build_dbg" if debug else "build")
     os.makedirs(bdir, exist_ok=True)
+    out = OUT.replace("libofb200.so", "libofb200_dbg.so") if debug else OUT
+    flags = FLAGS + (["-DOFB_DEBUG_BOUNDS=1"] if debug else [])
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "ofb200.h"))
     jobs = []
@@ -37,7 +41,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(bdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -50,14 +54,14 @@ def build(force=False, verbose=False):
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed for " + cmd[-3])
-    if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+    if force or jobs or _stale(out, objs):
+        cmd = [NVCC, "-shared", "-o", out] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -7,7 +7,9 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofb200.so")
+# OFB200_LIB selects another build of the same library (the debug build with device-side index assertions,
+# `python -m ofb200._build --debug` -> libofb200_dbg.so); there is still no CPU path behind it
+LIB_PATH = os.environ.get("OFB200_LIB") or os.path.join(_HERE, "libofb200.so")
 
 OFB_OK, OFB_E_INVALID, OFB_E_CUDA, OFB_E_NOMEM, OFB_E_UNSUPPORTED = 0, -1, -2, -3, -4
 VARIANT_NODE, VARIANT_EXP, VARIANT_SIM, VARIANT_MODULE = 0, 1, 2, 3

@@ -71,6 +71,22 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Debug build (-DOFB_DEBUG_BOUNDS=1, `python -m ofb200._build --debug` -> libofb200_dbg.so, selected with OFB200_LIB): the
+// index arithmetic of the kernels is checked where it is computed; a violation prints its location and traps, which
+// surfaces as a CUDA error of the call. compute-sanitizer is not available on the GPU pool, this is the substitute.
+#ifdef OFB_DEBUG_BOUNDS
+#define OFB_DEV_ASSERT(c)                                                                                              \
+    do {                                                                                                               \
+        if (!(c)) {                                                                                                    \
+            printf("OFB_DEV_ASSERT %s:%d: %s (block %d,%d,%d thread %d)\n", __FILE__, __LINE__, #c, (int)blockIdx.x,     \
+                   (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                                                \
+            __trap();                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+#else
+#define OFB_DEV_ASSERT(c) ((void)0)
+#endif
+
 enum { OFB_NSCRATCH = 25, OFB_NSTAGES = 5, OFB_NSTAGE_EV = 6, OFB_NFUNC_SLOTS = 32 };
 
 struct ofb_ctx {

@@ -60,7 +60,8 @@ __host__ __device__ void mc_load_params(const ofb_mc_step& s, McParams<T>& p)
 // (every saved sweep except sim_err_vs_num); R_out is then 0.
 template <class T, bool WANT_R = true>
 OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* __restrict__ sflow,
-                                         uint64_t trial, uint2 key, uint32_t step, double v_out[3], double& R_out)
+                                         const T* __restrict__ sconst, uint64_t trial, uint2 key, uint32_t step,
+                                         double v_out[3], double& R_out)
 {
     uint32_t tlo = (uint32_t)trial, thi = (uint32_t)(trial >> 32);
     T z0, z1, z2, z3;
@@ -71,7 +72,6 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
     mc_normals4<T>(tlo, thi, 1u, step, key, z0, z1, z2, z3);
     T t0 = P.t[0] + P.st * z0, t1 = P.t[1] + P.st * z1, t2 = P.t[2] + P.st * z2;
     T dh_rel = dh / P.h;
-    T dn0 = P.nh[0] - P.n[0], dn1 = P.nh[1] - P.n[1], dn2 = P.nh[2] - P.n[2];
 
     T m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, g0 = 0, g1 = 0, g2 = 0, accR = 0;
 #pragma unroll 2
@@ -92,8 +92,8 @@ OFB_HD void mc_trial(const McParams<T>& P, const T* __restrict__ spos, const T* 
         g0 -= nx * (py * bz - by); g1 -= nx * (bx - px * bz); g2 -= nx * (px * by - py * bx);
         if (WANT_R) {
             // analytic error bound, simulation.py:57-63 (xp = true position)
-            T v_e = dh_rel * (P.n[0] * px0 + P.n[1] * py0 + P.n[2]) + (dn0 * px0 + dn1 * py0 + dn2) +
-                    (P.n[0] * dpx + P.n[1] * dpy);
+            // (n . x and dn . x of the TRUE position do not depend on the trial: sconst, filled once per step)
+            T v_e = dh_rel * sconst[2 * j] + sconst[2 * j + 1] + (P.n[0] * dpx + P.n[1] * dpy);
             T e0 = dfx + (dpy * P.w[2]) + (py0 * dw2 - dw1) + dpx;
             T e1 = dfy + (-dpx * P.w[2]) + (dw0 - px0 * dw2) + dpy;
             T e2 = (dpx * P.w[1] - dpy * P.w[0]) + (px0 * dw1 - py0 * dw0);
@@ -128,6 +128,7 @@ mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const d
     __shared__ McParams<T> P;
     __shared__ T spos[2 * OFB_MC_MAX_POINTS];
     __shared__ T sflow[2 * OFB_MC_MAX_POINTS];
+    __shared__ T sconst[2 * OFB_MC_MAX_POINTS];     // per point: n . x, (n/|n| - n) . x of the true position (error bound R)
     __shared__ double red[MC_NSTAT][MC_THREADS / 32];
     int step = blockIdx.y;
     if (threadIdx.x == 0) mc_load_params<T>(steps[step], P);
@@ -137,11 +138,20 @@ mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const d
         sflow[i] = (T)flow[2 * (size_t)P.pos_offset + i];
     }
     __syncthreads();
+    if (WANT_R) {
+        const T dn0 = P.nh[0] - P.n[0], dn1 = P.nh[1] - P.n[1], dn2 = P.nh[2] - P.n[2];
+        for (int j = threadIdx.x; j < P.N; j += blockDim.x) {
+            const T px0 = spos[2 * j], py0 = spos[2 * j + 1];
+            sconst[2 * j] = P.n[0] * px0 + P.n[1] * py0 + P.n[2];
+            sconst[2 * j + 1] = dn0 * px0 + dn1 * py0 + dn2;
+        }
+        __syncthreads();
+    }
     double acc[MC_NSTAT] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < trials; k += stride) {
         double v[3], R;
-        mc_trial<T, WANT_R>(P, spos, sflow, trial_begin + k, key, (uint32_t)(step_id_base + step), v, R);
+        mc_trial<T, WANT_R>(P, spos, sflow, sconst, trial_begin + k, key, (uint32_t)(step_id_base + step), v, R);
         if (v_dump) {
             double* o = v_dump + ((size_t)step * trials + k) * 3;
             o[0] = v[0]; o[1] = v[1]; o[2] = v[2];

@@ -132,6 +132,7 @@ __device__ __forceinline__ void pyr_filter_tile(const uint8_t* tile, uint8_t* __
         // outputs ox..ox+3 need source columns 2ox-2 .. 2ox+8 = tile bytes 8tx+14 .. 8tx+24: words 2tx+3 .. 2tx+6
         // (local bytes j=0..15 <-> tile byte 8tx+12+j; taps of output k are j = 2+2k .. 6+2k);
         // output rows oy, oy+1 need tile rows 4ty .. 4ty+6
+        OFB_DEV_ASSERT((4 * ty + 6) * PS_PITCH + 4 * (2 * tx + 3 + 3) + 3 < PS_H * PS_PITCH);
         const uint32_t* t32 = (const uint32_t*)tile + (4 * ty) * (PS_PITCH / 4) + 2 * tx + 3;
         unsigned int hsum[7][4];
 #pragma unroll
@@ -155,6 +156,7 @@ __device__ __forceinline__ void pyr_filter_tile(const uint8_t* tile, uint8_t* __
                                  6u * hsum[2 * rr + 2][k];
                 packed |= ((v + 128u) >> 8) << (8 * k);
             }
+            OFB_DEV_ASSERT(oy + rr >= 0 && oy + rr < dh && ox >= 0 && ox < dw && (!vec_ok || ox + 3 < dpitch));
             uint8_t* drow = d + (size_t)(oy + rr) * dpitch + ox;
             if (vec_ok) *(uint32_t*)drow = packed;
             else

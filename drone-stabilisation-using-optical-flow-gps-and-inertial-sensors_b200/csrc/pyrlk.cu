@@ -217,6 +217,7 @@ lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restric
         }
     }
     if (lane == 0) {
+        OFB_DEV_ASSERT(feat >= 0 && feat < n && (gridDim.y == 1 || po < (size_t)(pair + 1) * pts_stride));   // (one pair: the stride is unused)
         next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
         status[po] = st ? 1 : 0;
         if (err) err[po] = st ? errv : 0.f;
@@ -261,6 +262,7 @@ __device__ __forceinline__ void load12(const uint8_t* __restrict__ img, int w, i
                                        unsigned int& o0, unsigned int& o1, unsigned int& o2)
 {
     const uint8_t* row = img + (size_t)Yr * pitch;
+    OFB_DEV_ASSERT(Yr >= 0 && (!colfast || (X0 >= 0 && X0 + 12 <= w)));
     if (colfast) {
         unsigned long long a = (unsigned long long)(row + X0);
         const unsigned int* q = (const unsigned int*)(a & ~3ull);
@@ -440,7 +442,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
             // sub-pixel): only the bilinear weights change then
             if (jx != cjx || jy != cjy) {
                 const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                OFB_DEV_ASSERT(!jrow || (jy + r >= 0 && jy + r < h)); load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
                 U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
                 U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 cjx = jx; cjy = jy;
@@ -473,7 +475,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
                 const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
                 if (jx != cjx || jy != cjy) {
                     const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-                    load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                    OFB_DEV_ASSERT(!jrow || (jy + r >= 0 && jy + r < h)); load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
                     U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
                     U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 }
@@ -486,6 +488,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
         }
     }
     if (lane == 0) {
+        OFB_DEV_ASSERT(feat >= 0 && feat < n && (gridDim.y == 1 || po < (size_t)(pair + 1) * pts_stride));   // (one pair: the stride is unused)
         next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
         status[po] = st ? 1 : 0;
         if (err) err[po] = st ? errv : 0.f;
@@ -662,7 +665,7 @@ lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restric
             const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
             if (jx != cjx || jy != cjy) {               // the patch rows stay in registers while the integer position holds
                 const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-                load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                OFB_DEV_ASSERT(!jrow || (jy + r >= 0 && jy + r < h)); load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
                 U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
                 U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 cjx = jx; cjy = jy;
@@ -699,7 +702,7 @@ lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restric
                 const int Wt = (w00 & 0xffff) | (w01 << 16), Wb = (w10 & 0xffff) | (w11 << 16);
                 if (jx != cjx || jy != cjy) {
                     const bool jcol = jx >= jlow && jx + 8 + 16 <= w, jrow = jy >= 0 && jy + 15 < h;
-                    load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
+                    OFB_DEV_ASSERT(!jrow || (jy + r >= 0 && jy + r < h)); load12(J, w, jpitch, jx + 8 * hh, jrow ? jy + r : refl101(jy + r, h), jcol, T0, T1, T2);
                     U0 = __shfl_down_sync(0xffffffffu, T0, 2); U1 = __shfl_down_sync(0xffffffffu, T1, 2);
                     U2 = __shfl_down_sync(0xffffffffu, T2, 2);
                 }
@@ -712,6 +715,7 @@ lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restric
         }
     }
     if (lane == 0) {
+        OFB_DEV_ASSERT(feat >= 0 && feat < n && (gridDim.y == 1 || po < (size_t)(pair + 1) * pts_stride));   // (one pair: the stride is unused)
         next_pts[2 * po] = nx; next_pts[2 * po + 1] = ny;
         status[po] = st ? 1 : 0;
         if (err) err[po] = st ? errv : 0.f;

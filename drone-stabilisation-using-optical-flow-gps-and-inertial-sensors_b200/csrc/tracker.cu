@@ -167,6 +167,7 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         for (int k = 0; k < OFB_SOLVE_THREADS / 32; ++k) { if (k < warp) off += wtot[k]; tot += wtot[k]; }
         if (keep) {
             const size_t o = base + off + __popc(bal & ((1u << lane) - 1u));
+            OFB_DEV_ASSERT(o >= (size_t)s * T.cap && o < (size_t)(s + 1) * T.cap);
             T.kept_prev[2 * o] = px; T.kept_prev[2 * o + 1] = py;
             T.kept_next[2 * o] = qx; T.kept_next[2 * o + 1] = qy;
         }
