@@ -55,6 +55,17 @@ __host__ __device__ void mc_load_params(const ofb_mc_step& s, McParams<T>& p)
     p.N = s.n_points; p.pos_offset = s.pos_offset;
 }
 
+// Per-point constants of the analytic error bound (simulation.py:57-58 evaluated at the TRUE position, which does not
+// depend on the trial): sconst[2j] = n . x_j, sconst[2j+1] = (n/|n| - n) . x_j. Filled once per step.
+template <class T>
+OFB_HD void mc_point_consts(const McParams<T>& P, const T* __restrict__ spos, int j, T* __restrict__ sconst)
+{
+    const T dn0 = P.nh[0] - P.n[0], dn1 = P.nh[1] - P.n[1], dn2 = P.nh[2] - P.n[2];
+    const T px0 = spos[2 * j], py0 = spos[2 * j + 1];
+    sconst[2 * j] = P.n[0] * px0 + P.n[1] * py0 + P.n[2];
+    sconst[2 * j + 1] = dn0 * px0 + dn1 * py0 + dn2;
+}
+
 // One trial of of_simulation (simulation.py:39-64).
 // WANT_R = false skips the analytic error bound R (simulation.py:56-64) for callers that only consume v_obs
 // (every saved sweep except sim_err_vs_num); R_out is then 0.
@@ -139,12 +150,7 @@ mc_sweep_kernel(const ofb_mc_step* __restrict__ steps, int step_id_base, const d
     }
     __syncthreads();
     if (WANT_R) {
-        const T dn0 = P.nh[0] - P.n[0], dn1 = P.nh[1] - P.n[1], dn2 = P.nh[2] - P.n[2];
-        for (int j = threadIdx.x; j < P.N; j += blockDim.x) {
-            const T px0 = spos[2 * j], py0 = spos[2 * j + 1];
-            sconst[2 * j] = P.n[0] * px0 + P.n[1] * py0 + P.n[2];
-            sconst[2 * j + 1] = dn0 * px0 + dn1 * py0 + dn2;
-        }
+        for (int j = threadIdx.x; j < P.N; j += blockDim.x) mc_point_consts<T>(P, spos, j, sconst);
         __syncthreads();
     }
     double acc[MC_NSTAT] = {0, 0, 0, 0, 0, 0, 0, 0};

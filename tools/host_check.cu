@@ -33,17 +33,21 @@ int main(int argc, char** argv)
         McParams<float> P; mc_load_params<float>(st, P);
         std::vector<float> p(2 * N), fl(2 * N);
         for (int i = 0; i < 2 * N; ++i) { p[i] = (float)pos[i]; fl[i] = (float)flow[i]; }
+        std::vector<float> pc(2 * N);
+        for (int j = 0; j < N; ++j) mc_point_consts<float>(P, p.data(), j, pc.data());
         for (uint32_t t = 0; t < ntr; ++t) {
             double v[4];
-            mc_trial<float>(P, p.data(), fl.data(), t, key, step, v, v[3]);
+            mc_trial<float>(P, p.data(), fl.data(), pc.data(), t, key, step, v, v[3]);
             fwrite(v, 8, 4, o);
         }
     }
     {
         McParams<double> P; mc_load_params<double>(st, P);
+        std::vector<double> pc(2 * N);
+        for (int j = 0; j < N; ++j) mc_point_consts<double>(P, pos.data(), j, pc.data());
         for (uint32_t t = 0; t < ntr; ++t) {
             double v[4];
-            mc_trial<double>(P, pos.data(), flow.data(), t, key, step, v, v[3]);
+            mc_trial<double>(P, pos.data(), flow.data(), pc.data(), t, key, step, v, v[3]);
             fwrite(v, 8, 4, o);
         }
     }
