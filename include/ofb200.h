@@ -287,7 +287,14 @@ int ofb_tracker_set_points(ofb_tracker* trk, const float* pts, const int* counts
  * device; imu: one sample per stream; v_prior: n_streams x 3 prior velocity for the r_tilde gate (NULL = the
  * stream's last solved velocity, cfg.v_init before the first solve; an all-zero prior skips the gate). Outputs (host or device; optional ones may be
  * NULL): results[n_streams]; pts_out n_streams x capacity x 2 and n_out[n_streams] = point sets after the step;
- * kept_prev / kept_next n_streams x capacity x 2 = the (old, new) positions the solve used (first n_kept). */
+ * kept_prev / kept_next n_streams x capacity x 2 = the (old, new) positions the solve used (first n_kept).
+ * Streams: on a context that owns its stream (ofb_ctx_create) the ingest + pyramid of the new frame run on a stream of
+ * the tracker, ordered behind the previous step's LK kernel only, so that they overlap that step's filter / solve /
+ * top-up; they are ordered behind everything on the context's stream whenever another call of this library enqueued
+ * work there since the previous step (a kernel launch, ofb_memcpy_async into device memory). Device-resident frames
+ * produced by other means must be complete when the call is made. Contexts on a caller's stream
+ * (ofb_ctx_create_on_stream) and contexts whose stream was handed out (ofb_ctx_stream) keep every operation on that
+ * stream. OFB_TRACKER_EARLY_PYR=0 in the environment disables the second stream. */
 int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t image_stride,
                      const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
                      float* pts_out, int* n_out, float* kept_prev, float* kept_next);
