@@ -98,12 +98,12 @@ struct ofb_ctx {
     // what a caller may have put on the stream besides API calls that launch kernels: asynchronous copies into device memory
     // (ofb_memcpy_async) and anything at all once the stream handle was handed out (ofb_ctx_stream). The tracker moves its
     // ingest to an internal stream only when neither happened since its previous step (see tracker_step_launches).
+    uint64_t async_writes = 0;
+    bool stream_exported = false;
     const int* lk_lo = nullptr;         // set around an ofb_lk_device call: per-pair first feature to track (LKParams::counts_lo)
     // streams of objects living on this context (a tracker's deferred top-up) that must be joined before the context's
     // stream counts as "done": ofb_ctx_sync, ofb_timer_stop and the memcpy calls wait for them (ofb_join_aux)
     std::vector<std::pair<cudaStream_t, cudaEvent_t>> aux_join;
-    uint64_t async_writes = 0;
-    bool stream_exported = false;
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: what this context has already
     // requested for each kernel that needs more than 48 KB (slot = FS_* below). Per context, hence per device.
     size_t func_smem[OFB_NFUNC_SLOTS] = {};
@@ -228,7 +228,8 @@ enum {
     FS_SELECT = 14,          // + {256, 512, 1024 threads}               (3 slots)
     FS_LK = 17,
     FS_PYR_TOP = 18,
-    FS_SELECT16 = 19         // + {256, 512, 1024 threads}: non-portable cluster size (16) allowed     (3 slots)
+    FS_SELECT16 = 19,        // + {256, 512, 1024 threads}: non-portable cluster size (16) allowed     (3 slots)
+    FS_MARCH_LEAN = 22       // + 2 * {bs 3, 7, 12} + write_map: the marching kernel without the general row loop (6 slots)
 };
 // Raises a kernel's dynamic shared-memory limit on the context's device when this context has not done so yet.
 template <class F>
