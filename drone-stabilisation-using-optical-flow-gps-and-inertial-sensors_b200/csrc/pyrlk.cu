@@ -230,7 +230,13 @@ lk_track_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restric
 // funnel shifts): no shared memory, no byte-granular traffic. Row r+1 of the window comes from lane+2 by
 // shuffle (the two lanes of row 15 only feed their neighbours). The Q14 bilinear taps of the image are two
 // dp2a (16-bit weights x u8 pixels) per pixel; a funnel shift yields the byte pairs of pixels k and k+2 at once.
-constexpr int LKF_WARPS = 4;
+// One feature = one warp = one CTA: the fast kernels use no shared memory and no block barrier, and features differ in
+// their number of Newton steps -- with four warps per CTA the three that finished early kept their slots until the
+// slowest one was done (0.854 -> 0.805 ms per 128 pairs with one; -DOFB_LKF_WARPS=n for A/B builds). 32 CTAs per SM.
+#ifndef OFB_LKF_WARPS
+#define OFB_LKF_WARPS 1
+#endif
+constexpr int LKF_WARPS = OFB_LKF_WARPS;
 
 __device__ __forceinline__ int dp2a_lo(int w16x2, unsigned int bytes, int c)
 {
@@ -310,7 +316,7 @@ __device__ __forceinline__ float warp_sum_exact_f(int v)
         }                                                                                         \
     }
 
-__global__ void __launch_bounds__(LKF_WARPS * 32, 8)
+__global__ void __launch_bounds__(LKF_WARPS * 32, 32 / LKF_WARPS)
 lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                      uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
                      int counts_stride, int n_uniform, size_t pts_stride)
@@ -511,7 +517,7 @@ lk_track_fast_kernel(LKParams P, const float* __restrict__ prev_pts, float* __re
 //     evaluation OpenCV uses is only needed there).
 __device__ __forceinline__ unsigned int prmt(unsigned int a, unsigned int b, unsigned int sel) { return __byte_perm(a, b, sel); }
 
-__global__ void __launch_bounds__(LKF_WARPS * 32, 8)
+__global__ void __launch_bounds__(LKF_WARPS * 32, 32 / LKF_WARPS)
 lk_track_fast2_kernel(const __grid_constant__ LKParams P, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                       uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ counts,
                       int counts_stride, int n_uniform, size_t pts_stride)

@@ -1,13 +1,7 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_tracker.py tests/test_gpu_pairs_mc.py -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu_r2c.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu_r2c.log; tail -12 gpurun_out/pytest_gpu_r2c.log
-OFB_LK_V1=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-mc --no-cpu > gpurun_out/bench_lkv1.log 2>&1; echo "exit $?"
-timeout 300 python bench.py --steps 10 --warmup 3 --no-mc --no-cpu > gpurun_out/bench_lkv2.log 2>&1; echo "exit $?"
-python - <<'PY'
-import json
-for f in ("bench_lkv1","bench_lkv2"):
-    try:
-        d=json.loads(open("gpurun_out/%s.log"%f).read().strip().split("\n")[-1])
-        print(f, round(d["value"]), "pairs/s", d["roofline"]["stage_ms"], "e2e", round(d["e2e"]["value"]), "trk", round(d["track_solve"]["value"]), d["check"])
-    except Exception as e: print(f, "ERR", e)
-PY
-bash tools/prof_eig.sh "lk_track" 1 prof_r2_lk
+timeout 900 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_tracker.py tests/test_gpu_random.py tests/test_gpu_pairs_mc.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python bench.py --workload c5 --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); l=d['lifecycle']; print('c5', d['value'], 'lifecycle', l['value'], 'bgr', l['bgr_frames']['value'])"
+for wl in c1 c4; do timeout 300 python bench.py --workload $wl --steps 50 --warmup 5 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print('$wl', d['value'], d['stage_ms_serial'], d['lifecycle_step']['resident_ms_per_frame'])"; done
