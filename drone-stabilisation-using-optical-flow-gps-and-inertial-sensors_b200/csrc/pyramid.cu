@@ -388,7 +388,8 @@ int ofb_pyr_build_from(ofb_ctx* ctx, ofb_pyr* p, int first_level)
         // (the in-CTA double buffering pays once a CTA owns several tiles; a level with fewer than ~4 tiles per
         // resident CTA runs one tile per CTA and relies on the 5 co-resident CTAs to overlap copy and filter)
         long long grid = (long long)ctx->sm_count * 5;
-        if (n_tiles < grid * 4) grid = n_tiles;
+        static const int persist_min = [] { const char* e = getenv("OFB_PYR_PERSIST_MIN"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
+        if (n_tiles < grid * persist_min) grid = n_tiles;
         if (grid == n_tiles) {
             // small level: latency-bound, one tile per CTA with direct loads
             dim3 g3(tiles_x, tiles_y, p->n_active);
