@@ -1,6 +1,6 @@
 timeout 600 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_random.py -m gpu -q -p no:cacheprovider -k "lk or LK or track or random or c4 or c5 or c1 or pyr" 2>&1 | tail -2
-for v in pf nopf pf nopf; do
-if [ $v == pf ]; then unset OFB200_LIB; else export OFB200_LIB=$PWD/drone-stabilisation-using-optical-flow-gps-and-inertial-sensors_b200/libofb200_nopf.so; fi
+for v in pf na pf na; do
+if [ $v == pf ]; then unset OFB200_LIB; else export OFB200_LIB=$PWD/drone-stabilisation-using-optical-flow-gps-and-inertial-sensors_b200/libofb200_na.so; fi
 timeout 300 python bench.py --workload c2 --steps 10 --warmup 3 --no-mc --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print('lk $v', round(d['value']), d['roofline']['stage_ms'], round(d['track_solve']['value']), d['lifecycle']['ms_per_frame'])"
