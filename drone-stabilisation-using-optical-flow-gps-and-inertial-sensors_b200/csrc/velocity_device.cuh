@@ -3,7 +3,9 @@
 #pragma once
 #include "math3.cuh"
 
+#ifndef OFB_SOLVE_THREADS
 #define OFB_SOLVE_THREADS 256
+#endif
 
 struct OfbSolveOut { double v[3]; double s[3]; double res; int rank; int count; };
 

@@ -1,7 +1,9 @@
-timeout 600 python -m pytest tests/test_gpu_vision.py tests/test_gpu_fullsize.py tests/test_gpu_random.py -m gpu -q -p no:cacheprovider -k "lk or LK or track or random or c4 or c5 or c1 or pyr" 2>&1 | tail -2
-for v in pf na pf na; do
-if [ $v == pf ]; then unset OFB200_LIB; else export OFB200_LIB=$PWD/drone-stabilisation-using-optical-flow-gps-and-inertial-sensors_b200/libofb200_na.so; fi
+for v in base s512 base s512; do
+if [ $v == base ]; then unset OFB200_LIB; else export OFB200_LIB=$PWD/drone-stabilisation-using-optical-flow-gps-and-inertial-sensors_b200/libofb200_$v.so; fi
+for wl in c1 c4; do timeout 300 python bench.py --workload $wl --steps 50 --warmup 5 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print('$v $wl', round(d['value'],4), d['stage_ms_serial']['solve'], round(d['lifecycle_step']['resident_ms_per_frame'],4))"; done
 timeout 300 python bench.py --workload c2 --steps 10 --warmup 3 --no-mc --no-cpu 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print('lk $v', round(d['value']), d['roofline']['stage_ms'], round(d['track_solve']['value']), d['lifecycle']['ms_per_frame'])"
+d=json.loads(sys.stdin.read().strip().split(chr(10))[-1]); print('$v c2', round(d['value']), d['roofline']['stage_ms']['solve'], round(d['track_solve']['value']), round(d['lifecycle']['ms_per_frame'],5))"
 done
