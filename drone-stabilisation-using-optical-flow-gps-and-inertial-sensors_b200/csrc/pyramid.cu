@@ -24,6 +24,10 @@ constexpr int PT_W = 64, PT_H = 32;                 // output tile
 constexpr int PS_W = 2 * PT_W + 32;                 // staged source columns: 2*X0-16 .. 2*X0+143 (10 x 16 bytes)
 constexpr int PS_H = 2 * PT_H + 3;                  // staged source rows:    2*Y0-2 .. 2*Y0+64
 constexpr int PS_PITCH = PS_W;                      // bytes, multiple of 16
+#ifndef OFB_PYR_THREADS
+#define OFB_PYR_THREADS 256
+#endif
+constexpr int PYR_THREADS = OFB_PYR_THREADS;        // threads of the two down-sampling kernels (the filter uses 128)
 
 __device__ __forceinline__ int refl101(int p, int len)
 {
@@ -90,7 +94,7 @@ __device__ __forceinline__ bool pyr_stage_tile(const CUtensorMap* tmap, bool use
     // the image edge gather bytes (independent loads: a border tile costs one memory latency, not one per byte)
     uint4* t128 = (uint4*)tile;
     constexpr int GPR = PS_W / 16;
-    for (int i = threadIdx.x; i < PS_H * GPR; i += 256) {
+    for (int i = threadIdx.x; i < PS_H * GPR; i += (int)blockDim.x) {
         const int r = i / GPR, c = i - r * GPR;
         const int yy = tiny ? refl101(sy0 + r, sh) : refl101_bf(sy0 + r, sh);
         const int gx0 = sx0 + 16 * c;
@@ -180,7 +184,7 @@ __device__ __forceinline__ void pyr_filter_tile(const uint8_t* tile, uint8_t* __
 
 // One tile per CTA, staged with direct loads (no mbarrier set-up): used for the small upper levels, which are
 // latency-bound launches.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PYR_THREADS)
 pyr_down_small_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t sstride, uint8_t* __restrict__ dst,
                       int dw, int dh, int dpitch, size_t dstride)
 {
@@ -289,7 +293,7 @@ ingest_bgr_pyr_kernel(const uint8_t* __restrict__ bgr, int w, int h, int bpitch,
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the whole batch with two shared-
 // memory stages: the TMA copy of tile i+1 is in flight while tile i is filtered.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PYR_THREADS)
 pyr_down_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                 size_t sstride, uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t dstride, int tiles_x, int tiles_y,
                 int n_tiles)
@@ -400,13 +404,13 @@ int ofb_pyr_build_from(ofb_ctx* ctx, ofb_pyr* p, int first_level)
         // fewer tiles -> one CTA per tile
         // (the in-CTA double buffering pays once a CTA owns several tiles; a level with fewer than ~4 tiles per
         // resident CTA runs one tile per CTA and relies on the 5 co-resident CTAs to overlap copy and filter)
-        long long grid = (long long)ctx->sm_count * 5;
+        long long grid = (long long)ctx->sm_count * (5 * 256 / PYR_THREADS);
         static const int persist_min = [] { const char* e = getenv("OFB_PYR_PERSIST_MIN"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
         if (n_tiles < grid * persist_min) grid = n_tiles;
         if (grid == n_tiles) {
             // small level: latency-bound, one tile per CTA with direct loads
             dim3 g3(tiles_x, tiles_y, p->n_active);
-            pyr_down_small_kernel<<<g3, 256, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss, p->base + p->level_off[l],
+            pyr_down_small_kernel<<<g3, PYR_THREADS, 0, ctx->stream>>>(s, p->w[l - 1], p->h[l - 1], sp, ss, p->base + p->level_off[l],
                                                               p->w[l], p->h[l], p->pitch[l], p->image_stride[l]);
             OFB_LAUNCH_CHECK(ctx);
             continue;
@@ -427,7 +431,7 @@ int ofb_pyr_build_from(ofb_ctx* ctx, ofb_pyr* p, int first_level)
                 use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
             }
         }
-        pyr_down_kernel<<<(unsigned int)grid, 256, 0, ctx->stream>>>(tmap, use_tma, s, p->w[l - 1], p->h[l - 1], sp, ss,
+        pyr_down_kernel<<<(unsigned int)grid, PYR_THREADS, 0, ctx->stream>>>(tmap, use_tma, s, p->w[l - 1], p->h[l - 1], sp, ss,
                                                                     p->base + p->level_off[l], p->w[l], p->h[l], p->pitch[l],
                                                                     p->image_stride[l], tiles_x, tiles_y, (int)n_tiles);
         OFB_LAUNCH_CHECK(ctx);
