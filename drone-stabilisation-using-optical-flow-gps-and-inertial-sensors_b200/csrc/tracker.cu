@@ -59,11 +59,17 @@ struct ofb_tracker {
     ofb_ctx* top_ctx = nullptr;
     cudaEvent_t ev_filter = nullptr, ev_top = nullptr, ev_join = nullptr;
     bool top_pending = false;          // a deferred top-up has not been joined into the context's stream yet
+    // split solve: with device-resident inputs and result records the fp64 solve of a step runs on its own stream beside
+    // the next frame's LK (track_filter_solve_kernel<1> / <2>); the next filter and the context's sync points wait for it
+    cudaStream_t sol_stream = nullptr;
+    cudaEvent_t ev_filt = nullptr, ev_sol = nullptr, ev_sol_join = nullptr;
+    bool sol_pending = false;
     int plain_steps = 0;               // steps run launch by launch since creation (scratch arenas are sized by them)
     uint64_t graph_steps = 0;
 };
 
 static cudaError_t tracker_join_topup(ofb_tracker* t);
+static cudaError_t tracker_join_solve(ofb_tracker* t);
 
 namespace {
 
@@ -111,6 +117,11 @@ __device__ __forceinline__ double r_tilde_point(double px, double py, double ux,
     return r;
 }
 
+// PART 0: filter + solve in one launch. PART 1: the filter alone (compaction, gates, counts, top-up decision -- all the next
+// step's LK needs); PART 2: the solve of a stream an earlier PART 1 launch compacted. The split lets the solve run beside
+// the next frame's LK on a stream of its own: nothing but the NEXT filter (its r_tilde gate uses the solved velocity) and
+// the reader of the result record depend on it.
+template <int PART>
 __global__ void __launch_bounds__(OFB_SOLVE_THREADS)
 track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, const double* __restrict__ v_prior,
                           ofb_track_result* __restrict__ out)
@@ -134,7 +145,8 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
     const float speed_thr = T.max_speed > 0 ? (float)(T.max_speed / im.d) : 0.f;
     const float dummy = (float)T.dummy;
     int kept = 0, tracked = 0;
-    for (int i0 = 0; i0 < n; i0 += OFB_SOLVE_THREADS) {
+    if (PART == 2) kept = T.kept[s];
+    for (int i0 = 0; PART != 2 && i0 < n; i0 += OFB_SOLVE_THREADS) {
         const int i = i0 + tid;
         bool st = false, keep = false;
         float px = 0, py = 0, qx = 0, qy = 0;
@@ -174,38 +186,43 @@ track_filter_solve_kernel(TrackerDev T, const ofb_imu_sample* __restrict__ imu, 
         kept += tot;
         __syncthreads();
     }
-    // tracked: every lane of a warp holds its warp's total; sum over warps
-    if (lane == 0) wtot[warp] = tracked;
-    __syncthreads();
-    tracked = 0;
+    if (PART != 2) {
+        // tracked: every lane of a warp holds its warp's total; sum over warps
+        if (lane == 0) wtot[warp] = tracked;
+        __syncthreads();
+        tracked = 0;
 #pragma unroll
-    for (int k = 0; k < OFB_SOLVE_THREADS / 32; ++k) tracked += wtot[k];
-    __syncthreads();                                                  // kept_* visible to the whole CTA
+        for (int k = 0; k < OFB_SOLVE_THREADS / 32; ++k) tracked += wtot[k];
+        __syncthreads();                                              // kept_* visible to the whole CTA
+    }
     OfbSolveOut o;
     const bool solve = T.have_prev && kept >= T.min_solve && kept > 0;
-    if (solve) {
+    if (PART != 1 && solve) {
         KeptLoader ld{T.kept_prev, T.kept_next, kept, (size_t)T.cap, T.cx, T.cy, T.ps, T.fs};
         o = ofb_block_solve(ld, s, T.variant, im.d, im.n, im.w, im.t, vp);    // vp: MODULE's per-point distances (of_module.py:125)
     }
     // the detector's per-image state and (for streams that will top up) its min-distance cell grid start clean
-    if (kept <= T.min_features)
+    if (PART != 2 && kept <= T.min_features)
         for (size_t i = tid; i < T.cell_stride; i += OFB_SOLVE_THREADS) T.cell_grid[(size_t)s * T.cell_stride + i] = -1;
     if (tid == 0) {
-        FeatImageState z; z.max_key = 0; z.n_cand = 0; z.n_out = 0; z.overflow = 0;
-        T.feat_state[s] = z;
-        ofb_track_result r;
-        for (int k = 0; k < 3; ++k) { r.v[k] = solve ? o.v[k] : 0.0; r.s[k] = solve ? o.s[k] : 0.0; }
-        r.res = solve ? o.res : 0.0; r.rank = solve ? o.rank : 0;
-        r.flags = solve ? OFB_TRACK_SOLVED : 0;
-        r.n_prev = n; r.n_tracked = tracked; r.n_kept = kept; r.n_added = 0; r.n_points = kept;
-        out[s] = r;
-        if (solve) { T.vlast[3 * s] = o.v[0]; T.vlast[3 * s + 1] = o.v[1]; T.vlast[3 * s + 2] = o.v[2]; }
-        const int need = kept <= T.min_features;
-        if (need && T.use_cond) cudaGraphSetConditional(T.cond, 1u);  // any stream that needs a top-up enables the branch
-        T.kept[s] = kept;
-        T.need[s] = need;
-        T.count[s] = (need && T.topup_mode == OFB_TOPUP_REPLACE) ? 0 : kept;    // of_module.py:86 replaces the set
-        T.count0[s] = T.count[s];                                                // (the top-up appends behind this)
+        ofb_track_result& r = out[s];                                 // (the two parts own disjoint fields of the record)
+        if (PART != 1) {
+            for (int k = 0; k < 3; ++k) { r.v[k] = solve ? o.v[k] : 0.0; r.s[k] = solve ? o.s[k] : 0.0; }
+            r.res = solve ? o.res : 0.0; r.rank = solve ? o.rank : 0;
+            r.flags = solve ? OFB_TRACK_SOLVED : 0;
+            if (solve) { T.vlast[3 * s] = o.v[0]; T.vlast[3 * s + 1] = o.v[1]; T.vlast[3 * s + 2] = o.v[2]; }
+        }
+        if (PART != 2) {
+            FeatImageState z; z.max_key = 0; z.n_cand = 0; z.n_out = 0; z.overflow = 0;
+            T.feat_state[s] = z;
+            r.n_prev = n; r.n_tracked = tracked; r.n_kept = kept; r.n_added = 0; r.n_points = kept;
+            const int need = kept <= T.min_features;
+            if (need && T.use_cond) cudaGraphSetConditional(T.cond, 1u);  // any stream that needs a top-up enables the branch
+            T.kept[s] = kept;
+            T.need[s] = need;
+            T.count[s] = (need && T.topup_mode == OFB_TOPUP_REPLACE) ? 0 : kept;    // of_module.py:86 replaces the set
+            T.count0[s] = T.count[s];                                                // (the top-up appends behind this)
+        }
     }
 }
 
@@ -404,6 +421,16 @@ extern "C" int ofb_tracker_destroy(ofb_tracker* t)
     t->pin_in.release(); t->pin_out.release();
     if (t->side_stream) cudaStreamDestroy(t->side_stream);
     if (t->pyr_stream) { cudaStreamSynchronize(t->pyr_stream); cudaStreamDestroy(t->pyr_stream); }
+    if (t->sol_stream) {
+        cudaStreamSynchronize(t->sol_stream);
+        if (t->ctx)
+            for (size_t i = 0; i < t->ctx->aux_join.size(); ++i)
+                if (t->ctx->aux_join[i].first == t->sol_stream) { t->ctx->aux_join.erase(t->ctx->aux_join.begin() + i); break; }
+        cudaStreamDestroy(t->sol_stream);
+    }
+    if (t->ev_filt) cudaEventDestroy(t->ev_filt);
+    if (t->ev_sol) cudaEventDestroy(t->ev_sol);
+    if (t->ev_sol_join) cudaEventDestroy(t->ev_sol_join);
     if (t->top_ctx) {
         cudaStreamSynchronize(t->top_ctx->stream);
         if (t->ctx)
@@ -459,11 +486,22 @@ extern "C" int ofb_tracker_set_points(ofb_tracker* t, const float* pts, const in
 }
 
 // order the context's stream behind a deferred top-up that is still pending (see ofb_tracker::top_ctx)
-static cudaError_t tracker_join_topup(ofb_tracker* t)
+static cudaError_t tracker_join_solve(ofb_tracker* t)
+{
+    if (!t->sol_pending) return cudaSuccess;
+    t->sol_pending = false;
+    return cudaStreamWaitEvent(t->ctx->stream, t->ev_sol, 0);
+}
+static cudaError_t tracker_join_topup_only(ofb_tracker* t)
 {
     if (!t->top_pending) return cudaSuccess;
     t->top_pending = false;
     return cudaStreamWaitEvent(t->ctx->stream, t->ev_top, 0);
+}
+static cudaError_t tracker_join_topup(ofb_tracker* t)             // the whole previous step: deferred top-up and split solve
+{
+    const cudaError_t e = tracker_join_solve(t);
+    return e != cudaSuccess ? e : tracker_join_topup_only(t);
 }
 
 // One step, launch by launch, on ctx->stream (also the body that is captured into a graph).
@@ -615,18 +653,46 @@ static int tracker_step_launches(ofb_tracker* t, const uint8_t* frames, int pitc
         // the previous step's top-up may still be running in the child context: the points that survived that step are
         // tracked now, what the top-up appended (positions count0 .. count) once it has finished
         OFB_TRY(lk(T.count0, nullptr));
-        OFB_CUDA(tracker_join_topup(t));
+        OFB_CUDA(tracker_join_topup_only(t));
         OFB_TRY(lk(count, T.count0));
     } else {
-        OFB_CUDA(tracker_join_topup(t));
+        OFB_CUDA(tracker_join_topup_only(t));
         if (t->have_prev) OFB_TRY(lk(count, nullptr));
     }
     t->lk_recorded = false;
     if (early && t->have_prev) { OFB_CUDA(cudaEventRecord(t->ev_lk, ctx->stream)); t->lk_recorded = true; }
     // 3.+4. status filter, gates, solve; the compacted new positions become the point set (Pn)
-    track_filter_solve_kernel<<<S, OFB_SOLVE_THREADS, 0, ctx->stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
-                                                                        (ofb_track_result*)o[0].dev);
-    OFB_LAUNCH_CHECK(ctx);
+    // (the previous step's solve wrote the prior velocity of this step's gate and read the buffers this filter overwrites)
+    OFB_CUDA(tracker_join_solve(t));
+    bool split = false;
+    {
+        const char* se = getenv("OFB_TRACKER_SPLIT_SOLVE");
+        split = early && t->have_prev && ofb_is_device_ptr(results) && ofb_is_device_ptr(imu) && (!v_prior || ofb_is_device_ptr(v_prior)) &&
+                !(se && se[0] == '0');
+    }
+    if (split) {
+        if (!t->sol_stream) {
+            OFB_CUDA(cudaStreamCreateWithFlags(&t->sol_stream, cudaStreamNonBlocking));
+            OFB_CUDA(cudaEventCreateWithFlags(&t->ev_filt, cudaEventDisableTiming));
+            OFB_CUDA(cudaEventCreateWithFlags(&t->ev_sol, cudaEventDisableTiming));
+            OFB_CUDA(cudaEventCreateWithFlags(&t->ev_sol_join, cudaEventDisableTiming));
+            ctx->aux_join.push_back(std::make_pair(t->sol_stream, t->ev_sol_join));
+        }
+        track_filter_solve_kernel<1><<<S, OFB_SOLVE_THREADS, 0, ctx->stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
+                                                                               (ofb_track_result*)o[0].dev);
+        OFB_LAUNCH_CHECK(ctx);
+        OFB_CUDA(cudaEventRecord(t->ev_filt, ctx->stream));
+        OFB_CUDA(cudaStreamWaitEvent(t->sol_stream, t->ev_filt, 0));
+        track_filter_solve_kernel<2><<<S, OFB_SOLVE_THREADS, 0, t->sol_stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
+                                                                                 (ofb_track_result*)o[0].dev);
+        OFB_LAUNCH_CHECK(ctx);
+        OFB_CUDA(cudaEventRecord(t->ev_sol, t->sol_stream));
+        t->sol_pending = true;
+    } else {
+        track_filter_solve_kernel<0><<<S, OFB_SOLVE_THREADS, 0, ctx->stream>>>(T, (const ofb_imu_sample*)dimu, (const double*)dvp,
+                                                                               (ofb_track_result*)o[0].dev);
+        OFB_LAUNCH_CHECK(ctx);
+    }
     bool host_out = false;
     auto copy_out = [&](float* dst, const float* src) -> int {
         if (!dst) return OFB_OK;
