@@ -294,7 +294,10 @@ int ofb_tracker_set_points(ofb_tracker* trk, const float* pts, const int* counts
  * work there since the previous step (a kernel launch, ofb_memcpy_async into device memory). Device-resident frames
  * produced by other means must be complete when the call is made. Contexts on a caller's stream
  * (ofb_ctx_create_on_stream) and contexts whose stream was handed out (ofb_ctx_stream) keep every operation on that
- * stream. OFB_TRACKER_EARLY_PYR=0 in the environment disables the second stream. */
+ * stream. OFB_TRACKER_EARLY_PYR=0 in the environment disables the second stream. With device-resident frames, IMU samples and
+ * result records the fp64 solve of a step also runs on a stream of its own, beside the next frame's LK: the records are
+ * complete after ofb_ctx_sync / ofb_timer_stop / ofb_memcpy* on the context (they join that stream), or after the next step
+ * of the tracker has been synchronised; OFB_TRACKER_SPLIT_SOLVE=0 disables it. */
 int ofb_tracker_step(ofb_tracker* trk, const uint8_t* frames, int pitch, size_t image_stride,
                      const ofb_imu_sample* imu, const double* v_prior, ofb_track_result* results,
                      float* pts_out, int* n_out, float* kept_prev, float* kept_next);
