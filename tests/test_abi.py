@@ -63,3 +63,20 @@ def test_no_cpu_fallback():
         ofb200.solve_lgs([[0.1, 0.2], [0.3, 0.1], [0.0, 0.4]], [[0, 0]] * 3, 1.0, [0, 0, 1], [0, 0, 0])
     with pytest.raises(ofb200.OfbError):
         ofb200.goodFeaturesToTrack(__import__("numpy").zeros((32, 32), "uint8"), 10, 0.01, 5)
+
+
+def test_library_path_override(tmp_path):
+    """OFB200_LIB selects another build of the library (the debug build with device-side index assertions); a path that
+    does not exist must fail loudly -- there is no fallback to the default build or to the CPU."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from ofb200 import _lib; print(_lib.LIB_PATH); "
+            "lib = _lib.load(); print(lib.ofb_version())" % ROOT)
+    env = dict(os.environ)
+    from ofb200 import _lib
+    env["OFB200_LIB"] = _lib.LIB_PATH if not os.environ.get("OFB200_LIB") else os.environ["OFB200_LIB"]
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split()[-1] == "100", out.stderr[-400:]
+    env["OFB200_LIB"] = str(tmp_path / "no_such_build.so")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode != 0 and "not built" in (out.stderr + out.stdout)
